@@ -1,0 +1,149 @@
+"""Known-answer tests that pin the CPU oracle; no GPU, no reference."""
+import numpy as np
+import pytest
+
+from oracle import fem_oracle as fo
+
+
+def test_mesh_counts_and_order():
+    m = fo.box_mesh((0, 0, 0), (1, 0.2, 0.2), 4, 3, 2)
+    assert m.coords.shape == (5 * 4 * 3, 3) and m.cells.shape == (6 * 24, 4)
+    # vertex id = iz*(nx+1)*(ny+1) + iy*(nx+1) + ix, x fastest
+    assert np.array_equal(m.coords[7], [0.5, 0.2 * 1 / 3 if False else (1 * 0.2) / 3, 0.0])
+    # first grid cell, generation order, DOLFIN BoxMesh tets
+    v = [0, 1, 5, 6, 20, 21, 25, 26]
+    expect = [[v[a] for a in t] for t in fo.BOX_TETS]
+    assert m.cells_raw[:6].tolist() == expect
+    assert np.all(np.diff(m.cells, axis=1) > 0)
+    vol, _ = fo._gradients(m)
+    assert np.allclose(vol.sum(), 1 * 0.2 * 0.2) and np.allclose(vol, vol[0])
+    r = fo.rectangle_mesh(0, 0, 1, 1, 3, 2)
+    assert r.cells_raw[:2].tolist() == [[0, 1, 5], [0, 4, 5]]
+    i = fo.interval_mesh(100, 0.0, 2.0)
+    assert i.coords[-1, 0] == 2.0 and i.coords[37, 0] == 0.0 + (2.0 / 100) * 37
+
+
+def test_coordinate_expressions_differ_2d_vs_3d():
+    # A.1: a + ((b-a)/n)*i (2D) vs a + (i*(b-a))/n (3D) differ in the last bit for non-dyadic n
+    r = fo.rectangle_mesh(0, 0, 0.2, 0.2, 10, 10).coords[:11, 0]
+    b = fo.box_mesh((0, 0, 0), (0.2, 0.2, 0.2), 10, 1, 1).coords[:11, 0]
+    assert np.max(np.abs(r - b)) < 1e-16 and np.any(r != b)
+    assert fo.box_mesh((0, 0, 0), (1, 0.2, 0.2), 320, 1, 1).coords[320, 0] == 1.0
+
+
+def test_stencil_facts_3d():
+    # (vi): interior rows of K are the 7-point Laplacian, M has the 15-point Kuhn weights
+    n, h = 4, 0.25
+    m = fo.box_mesh((0, 0, 0), (1, 1, 1), n, n, n)
+    K, M = fo.assemble_stiffness_mass(m)
+    c = 2 + 5 * 2 + 25 * 2
+    rowK = K[c].toarray().ravel()
+    rowM = M[c].toarray().ravel() / h ** 3
+    off = lambda dx, dy, dz: c + dx + 5 * dy + 25 * dz
+    assert np.isclose(rowK[c], 6 * h) and np.isclose(rowK[off(1, 0, 0)], -h)
+    assert np.isclose(rowK[off(1, 1, 0)], 0) and np.isclose(rowK[off(1, 1, 1)], 0)
+    assert np.isclose(rowM[c], 0.4) and np.isclose(rowM[off(1, 0, 0)], 0.05)
+    assert np.isclose(rowM[off(1, 1, 0)], 1 / 30) and np.isclose(rowM[off(-1, -1, -1)], 0.05)
+    assert np.isclose(rowM[off(1, -1, 0)], 0) and np.isclose(rowM.sum(), 1.0)
+    assert np.count_nonzero(np.abs(rowM) > 1e-14) == 15
+
+
+def test_stencil_facts_2d():
+    m = fo.rectangle_mesh(0, 0, 1, 1, 4, 4)
+    K, M = fo.assemble_stiffness_mass(m)
+    c = 12
+    rk, rm = K[c].toarray().ravel(), M[c].toarray().ravel() * 16
+    assert np.isclose(rk[c], 4) and np.isclose(rk[c + 1], -1) and np.isclose(rk[c + 6], 0)
+    assert np.isclose(rm[c], 0.5) and np.isclose(rm[c + 6], 1 / 12) and np.isclose(rm[c + 4], 0)
+
+
+def test_heat_1d_steady_linear():
+    f = fo.solve_heat(1, [2.0], [100], 1.0, T_left=20.0, T_right=0.0, steady=True)
+    x = f.coords[:, 0]
+    assert np.allclose(f.values[0], 20.0 * (1 - x / 2.0), atol=1e-11)
+
+
+def test_heat_1d_sine_decay_closed_form():
+    # (iv-a): sin(jπx/L) is an eigenvector of M and K in 1D => exact per-step decay factor
+    L, nx, dt, kappa, j = 2.0, 64, 0.01, 1.0, 3
+    h = L / nx
+    mesh = fo.interval_mesh(nx, 0, L)
+    K, M = fo.assemble_stiffness_mass(mesh)
+    x = mesh.coords[:, 0]
+    u0 = np.sin(j * np.pi * x / L)
+    th = j * np.pi * h / L
+    lamM, lamK = h / 6 * (4 + 2 * np.cos(th)), (2 - 2 * np.cos(th)) / h
+    A, _ = fo.apply_bc_rowwise((M + dt * kappa * K).tocsr(), np.zeros(nx + 1), np.array([0, nx]), np.zeros(2))
+    b = M @ u0
+    b[[0, nx]] = 0
+    u1 = fo.lu_solve(A, b)
+    assert np.allclose(u1[1:-1], lamM / (lamM + dt * kappa * lamK) * u0[1:-1], atol=1e-13)
+
+
+def test_heat_rowwise_equals_symmetric():
+    a = fo.solve_heat(3, [1, 1, 1], [6, 5, 4], 1.0, T_initial=20.0, num_steps=3, T_boundary=2.0)
+    b = fo.solve_heat(3, [1, 1, 1], [6, 5, 4], 1.0, T_initial=20.0, num_steps=3, T_boundary=2.0, symmetric=True)
+    assert fo.rel_l2(a.values, b.values) < 1e-13
+    assert a.values.shape == (4, 7 * 6 * 5) and a.times[-1] == 3 * 0.01
+
+
+def test_heat_boundary_sets():
+    f = fo.solve_heat(3, [1, 1, 1], [4, 3, 2], 1.0, num_steps=0)
+    assert f.aux["bc_dofs"].size == 5 * 4 * 3 - 3 * 2 * 1
+    # directional: other_faces excludes vertices on x=0 / x=Lx (topological facet rule)
+    g = fo.solve_heat(3, [1, 1, 1], [4, 3, 2], 1.0, num_steps=0, T_side=5.0)
+    ix = g.aux["bc_dofs"] % 5
+    assert ix.min() == 1 and ix.max() == 3
+    h = fo.solve_heat(3, [1, 1, 1], [2, 3, 2], 1.0, num_steps=0, T_side=5.0)
+    assert h.aux["bc_dofs"].size == 0      # nx=2: every side facet touches an x-end
+
+
+def test_bar_1d_nodal_exact():
+    # (ii): u = f/(EA) (L x - x²/2) exactly at the nodes
+    L, nx, E, A, f = 1.5, 40, 210e9, 2.0, 1e6
+    r = fo.solve_elasticity(1, [L], [nx], E, body=[f], quantity="strain", area=A)
+    x = r.coords[:, 0]
+    assert np.allclose(r.aux["u"][:, 0], f / (E * A) * (L * x - x * x / 2), rtol=1e-10, atol=1e-17)
+    # cell strain is exact at cell midpoints; projection reproduces it in the interior to O(h²)
+    assert np.allclose(r.values[0][5:-5], f / (E * A) * (L - x[5:-5]), rtol=1e-3)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_zero_body_force_zero_von_mises(dim):
+    # (iii) docstring fenics_mcp_server.py:2639-2642
+    r = fo.solve_elasticity(dim, [1, 0.5, 0.5][:dim], [6, 4, 3][:dim], 210e9, 0.3)
+    assert np.all(r.values == 0.0)
+
+
+def test_patch_test_linear_displacement():
+    # (v): a linear displacement field has zero residual at nodes whose patch is complete
+    m = fo.box_mesh((0, 0, 0), (1, 0.5, 0.25), 4, 4, 4)
+    lam, mu = fo.lame(210e9, 0.3, 3)
+    A = fo.assemble_elasticity(m, lam, mu)
+    G = np.array([[1e-3, 2e-4, 0], [-1e-4, 5e-4, 3e-4], [2e-4, 0, -4e-4]])
+    u = (m.coords @ G.T).ravel()
+    r = (A @ u).reshape(-1, 3)
+    ijk = np.stack(np.unravel_index(np.arange(m.nv), (5, 5, 5)), axis=1)
+    interior = np.all((ijk > 0) & (ijk < 4), axis=1)
+    assert np.abs(r[interior]).max() < 1e-12 * A.diagonal().max() * 1e-3
+    vm = fo.von_mises_cells(m, u.reshape(-1, 3), lam, mu, "stress")
+    assert np.allclose(vm, vm[0], rtol=1e-10)
+
+
+def test_cantilever_sane():
+    # A.7: 40x8x8 beam tip deflection ≈ -1.307e-5 (Euler-Bernoulli -1.366e-5)
+    r = fo.solve_elasticity(3, [1, 0.2, 0.2], [40, 8, 8], 210e9, 0.3, body=[0, 0, -76518.0])
+    uz = r.aux["u"][:, 2]
+    assert abs(uz.min() / -1.3072e-5 - 1) < 1e-3
+    assert abs(r.values.max() / 1.1188e6 - 1) < 1e-3     # L2 projection may undershoot below 0
+
+
+def test_project_p2_reproduces_quadratic_moments():
+    # P2 interpolation of a quadratic is exact => projection == L2 projection of the function
+    m = fo.rectangle_mesh(0, 0, 1, 1, 6, 5)
+    fn = lambda x: 1 + x[:, 0] ** 2 - x[:, 0] * x[:, 1]
+    lin = lambda x: 2 - x[:, 0] + 3 * x[:, 1]
+    assert np.allclose(fo.project_p2_expression(m, lin), lin(m.coords), atol=1e-12)
+    u = fo.project_p2_expression(m, fn)
+    _, M = fo.assemble_stiffness_mass(m)
+    assert np.isclose((M @ u).sum(), 1 + 1 / 3 - 1 / 4)
