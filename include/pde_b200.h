@@ -1,0 +1,182 @@
+/*
+ * pde_b200.h — C ABI of the B200-native structured-mesh P1 solver (libpde_b200.so).
+ *
+ * This is the drop-in boundary below the Python host layer.  Each entry point names the
+ * reference interface it replaces (file:line under /root/reference/fenics_mcp_server.py;
+ * the arithmetic itself lives in DOLFIN 2019.1.0 + PETSc, which the reference calls there).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; pde_last_error() gives the
+ *     thread-local message.  Nothing is ever printed to stdout (the MCP server owns it).
+ *   - the caller owns all host buffers; the library owns device memory behind pde_ctx.
+ *   - plain pointers and sizes only; no callbacks; FP64 everywhere; indices int32 unless
+ *     stated (global offsets int64).
+ *   - dof order of every exported array is the NATURAL lattice order (vertex id =
+ *     iz*(nx+1)*(ny+1) + iy*(nx+1) + ix), i.e. DOLFIN with reorder_dofs_serial=False.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef PDE_B200_H
+#define PDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pde_ctx pde_ctx;
+
+/* ---- context / errors ------------------------------------------------------------- */
+const char* pde_last_error(void);
+int pde_version(void);
+/* one context per GPU (one process per GPU under torchrun; a process may hold several) */
+int pde_ctx_create(int device, pde_ctx** out);
+int pde_ctx_destroy(pde_ctx* ctx);
+/* number of kernels launched through this context since creation (bench "gpu_launches") */
+int64_t pde_ctx_launch_count(pde_ctx* ctx);
+int pde_ctx_sync(pde_ctx* ctx);
+/* CUDA-event timer on the context's compute stream */
+int pde_timer_start(pde_ctx* ctx);
+int pde_timer_stop(pde_ctx* ctx, double* elapsed_ms);
+
+/* ---- multi-GPU: slab partition along the slowest axis, NCCL over NVLink ------------- */
+/* libnccl.so.2 is dlopen()ed from `libnccl_path` (NULL: default search path). */
+int pde_nccl_unique_id(const char* libnccl_path, void* id128 /* 128 bytes out */);
+int pde_comm_init(pde_ctx* ctx, int rank, int world, const void* id128, const char* libnccl_path);
+
+/* ---- meshes, dof maps, boundary sets (bit-exact rows a2-a4 of SURVEY §8) ------------- */
+/* IntervalMesh :229,1516 / RectangleMesh :369,1648 / BoxMesh :533,1803.
+ * dim in {1,2,3}; n[k] cells along axis k; domain [0,L[k]].  Generated on the GPU. */
+int pde_mesh_counts(int dim, const int32_t n[3], int64_t* nverts, int64_t* ncells);
+int pde_mesh_coords(pde_ctx* ctx, int dim, const int32_t n[3], const double L[3],
+                    double* coords /* [nverts][dim] */);
+/* sorted=0: generation order of each cell's vertices; sorted=1: after mesh.order() */
+int pde_mesh_cells(pde_ctx* ctx, int dim, const int32_t n[3], int sorted,
+                   int32_t* cells /* [ncells][dim+1] */);
+/* FunctionSpace(mesh,"P",1) :230,370,535 (ncomp=1) / VectorFunctionSpace :1649,1804.
+ * layout 0: blocked (c*nverts+v, UFC numbering); 1: interleaved (ncomp*v+c). */
+int pde_dofmap_cells(pde_ctx* ctx, int dim, const int32_t n[3], int ncomp, int layout,
+                     int32_t* cell_dofs /* [ncells][ncomp*(dim+1)] */);
+
+/* Dirichlet specification = the reference's DirichletBC lists.
+ * face order: x=0, x=L, then the remaining faces of the present axes (y=0,y=L,z=0,z=L). */
+typedef struct pde_bc {
+  int32_t face_on[6];
+  double face_val[6];
+  int32_t side_excludes_xends; /* other_faces predicate :613-616: side faces skip ix=0 / ix=nx */
+} pde_bc;
+/* mask[v] = 1 where vertex v carries a Dirichlet value; vals[v] its value (0 elsewhere) */
+int pde_boundary_mask(pde_ctx* ctx, int dim, const int32_t n[3], const pde_bc* bc,
+                      uint8_t* mask /* [nverts] */, double* vals /* [nverts] or NULL */);
+
+/* ---- solver controls ------------------------------------------------------------------ */
+enum { PDE_PRECOND_JACOBI = 0, PDE_PRECOND_GMG = 1, PDE_PRECOND_AUTO = 2 };
+
+typedef struct pde_solver_opts {
+  double rtol;          /* ||r|| <= rtol*||b||; reference = direct LU, north-star rtol 1e-10 */
+  int32_t max_iters;
+  int32_t precond;      /* PDE_PRECOND_* */
+  int32_t cheby_degree; /* GMG smoother sweeps per side (default 2) */
+  int32_t check_every;  /* host convergence poll interval in iterations */
+  double cheby_ratio;   /* smoothing interval [lmax/ratio, lmax] */
+  int32_t reserved[4];
+} pde_solver_opts;
+void pde_solver_opts_default(pde_solver_opts* o);
+
+typedef struct pde_stats {
+  int64_t ndofs;         /* global dofs of the linear system(s) */
+  int64_t iters_total;   /* PCG iterations over all solves of the call */
+  int32_t solves;        /* linear solves performed */
+  int32_t converged;     /* 1 if every solve reached rtol */
+  int32_t levels;        /* multigrid levels used (1 = Jacobi) */
+  int32_t reserved;
+  double final_relres;   /* last solve: ||r||/||b|| (recurrence) */
+  double true_relres;    /* last solve: ||b - A x||/||b|| recomputed */
+  double solve_ms;       /* device time of the solver region (CUDA events) */
+  double setup_ms;
+  int64_t launches;      /* kernels launched by this call */
+} pde_stats;
+
+/* ---- heat: _solve_heat_{1,2,3}d_raw :204-338, 345-468, 475-762 (box, uniform kappa) ---- */
+enum { PDE_IC_CONSTANT = 0, PDE_IC_ZERO = 1, PDE_IC_COSINE = 2, PDE_IC_SINE = 3, PDE_IC_ARRAY = 4 };
+
+typedef struct pde_heat_params {
+  int32_t dim;
+  int32_t n[3];
+  double L[3];
+  double diffusivity;
+  double dt;
+  int32_t num_steps;
+  int32_t steady;
+  double source_value;       /* 0 when source_type == "none" */
+  int32_t initial_type;      /* PDE_IC_* */
+  int32_t snapshot_stride;   /* keep every k-th step (1 = the reference's behaviour) */
+  double T_initial;
+  double initial_amplitude;
+  double initial_wavenumber;
+  pde_bc bc;
+} pde_heat_params;
+
+/* values_out: [nsnap][nverts] natural order, nsnap = 1 + num_steps/stride (steady: 1);
+ * times_out: [nsnap]; u0 (PDE_IC_ARRAY only): [nverts] host initial field. */
+int pde_heat_solve(pde_ctx* ctx, const pde_heat_params* p, const pde_solver_opts* o,
+                   const double* u0, double* values_out, double* times_out, pde_stats* st);
+
+/* resident time stepper (bench / large runs): state stays in HBM between calls */
+typedef struct pde_heat_state pde_heat_state;
+int pde_heat_open(pde_ctx* ctx, const pde_heat_params* p, const pde_solver_opts* o,
+                  pde_heat_state** out);
+int pde_heat_set_state(pde_heat_state* s, const double* u_host /* [local nverts] */);
+int pde_heat_step(pde_heat_state* s, int nsteps, pde_stats* st);
+int pde_heat_get_state(pde_heat_state* s, double* u_host /* [local nverts] */);
+int64_t pde_heat_local_nverts(pde_heat_state* s);
+int pde_heat_close(pde_heat_state* s);
+
+/* ---- elasticity: _solve_elasticity_{1,2,3}d_static :1470-1587, 1593-1743, 1749-1892 ---- */
+typedef struct pde_elast_params {
+  int32_t dim;
+  int32_t n[3];
+  double L[3];
+  double E;
+  double nu;
+  double body[3];
+  int32_t quantity;       /* 0 = stress, 1 = strain */
+  int32_t plane_stress;   /* 2D only */
+  double area;            /* 1D only */
+} pde_elast_params;
+
+/* field_out: [nverts] projected von-Mises (1D: axial) stress/strain, natural order.
+ * disp_out: optional [nverts][dim] displacement (never exported by the reference). */
+int pde_elasticity_solve(pde_ctx* ctx, const pde_elast_params* p, const pde_solver_opts* o,
+                         double* field_out, double* disp_out, pde_stats* st, pde_stats* st_proj);
+
+/* ---- operator-level entry points (parity tests and micro-benchmarks) -------------------- */
+enum { PDE_OP_HEAT = 0, PDE_OP_MASS = 1, PDE_OP_STIFFNESS = 2, PDE_OP_ELASTICITY = 3 };
+
+typedef struct pde_op_params {
+  int32_t kind;       /* PDE_OP_* */
+  int32_t dim;
+  int32_t n[3];
+  double L[3];
+  double alpha;       /* heat: A = alpha*M + beta*K */
+  double beta;
+  double lam, mu;     /* elasticity */
+  pde_bc bc;          /* rows at Dirichlet vertices are masked to zero */
+  int32_t variant;    /* 0 = auto (fastest kernel), 1 = generic table kernel */
+} pde_op_params;
+
+/* host-only: interior/boundary stencil table [27][15][ncomp*ncomp] (no GPU needed) */
+int pde_op_table(const pde_op_params* p, double* table, int32_t* ncomp);
+/* y = A x on the device; x,y host arrays [ncomp][nverts] (blocked), natural order */
+int pde_op_apply(pde_ctx* ctx, const pde_op_params* p, const double* x, double* y);
+/* time `reps` device-resident applications (+fused dot); returns mean ms per apply */
+int pde_op_bench(pde_ctx* ctx, const pde_op_params* p, int reps, int warmup, double* ms_per_apply,
+                 int64_t* ndofs);
+/* solve A x = b (symmetric Dirichlet elimination) from host arrays; PCG per `o` */
+int pde_op_solve(pde_ctx* ctx, const pde_op_params* p, const pde_solver_opts* o, const double* b,
+                 double* x, pde_stats* st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDE_B200_H */

@@ -1,0 +1,618 @@
+// extern "C" entry points of libpde_b200.so (see include/pde_b200.h for the reference interface each
+// one replaces).  No torch types, no callbacks, no stdout.
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "solver.cuh"
+
+int comm_destroy(pde_ctx* c);
+
+// ---- context ----------------------------------------------------------------------------------
+extern "C" int pde_ctx_create(int device, pde_ctx** out) {
+  if (!out) PDE_FAIL("null out pointer");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    PDE_FAIL(std::string("no CUDA device available (this library has no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) PDE_FAIL("device index out of range");
+  CUDA_OK(cudaSetDevice(device));
+  pde_ctx* c = new (std::nothrow) pde_ctx();
+  if (!c) PDE_FAIL("out of host memory");
+  c->device = device;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&c->ev0));
+  CUDA_OK(cudaEventCreate(&c->ev1));
+  CUDA_OK(cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming));
+  CUDA_OK(cudaMalloc(&c->red.partials, sizeof(double) * RED_MAX_BLOCKS * RED_MAX_VALS));
+  CUDA_OK(cudaMalloc(&c->red.counter, sizeof(unsigned)));
+  CUDA_OK(cudaMemset(c->red.counter, 0, sizeof(unsigned)));
+  CUDA_OK(cudaMalloc(&c->scal, sizeof(double) * S_NSLOTS));
+  CUDA_OK(cudaMemset(c->scal, 0, sizeof(double) * S_NSLOTS));
+  CUDA_OK(cudaHostAlloc(&c->h_scal, sizeof(double) * S_NSLOTS, cudaHostAllocDefault));
+  *out = c;
+  return 0;
+}
+
+extern "C" int pde_ctx_destroy(pde_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  comm_destroy(c);
+  cudaFree(c->red.partials);
+  cudaFree(c->red.counter);
+  cudaFree(c->scal);
+  cudaFreeHost(c->h_scal);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev_poll);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+extern "C" int64_t pde_ctx_launch_count(pde_ctx* c) { return c ? c->launches : 0; }
+extern "C" int pde_ctx_sync(pde_ctx* c) {
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int pde_timer_start(pde_ctx* c) {
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  return 0;
+}
+extern "C" int pde_timer_stop(pde_ctx* c, double* ms) {
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float f = 0;
+  CUDA_OK(cudaEventElapsedTime(&f, c->ev0, c->ev1));
+  if (ms) *ms = f;
+  return 0;
+}
+
+struct DevMem {
+  void* p = nullptr;
+  ~DevMem() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    CUDA_OK(cudaMalloc(&p, bytes ? bytes : 8));
+    return 0;
+  }
+};
+
+static int d2h(pde_ctx* c, void* dst, const void* src, size_t bytes) {
+  CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+static int h2d(pde_ctx* c, void* dst, const void* src, size_t bytes) {
+  CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- meshes -------------------------------------------------------------------------------------
+extern "C" int pde_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* coords) {
+  if (!c) PDE_FAIL("null context");
+  CUDA_OK(cudaSetDevice(c->device));
+  int64_t nv, nc;
+  PDE_OK(pde_mesh_counts(dim, n, &nv, &nc));
+  DevMem d;
+  PDE_OK(d.alloc(sizeof(double) * nv * dim));
+  PDE_OK(launch_mesh_coords(c, dim, n, L, (double*)d.p));
+  return d2h(c, coords, d.p, sizeof(double) * nv * dim);
+}
+
+extern "C" int pde_dofmap_cells(pde_ctx* c, int dim, const int32_t n[3], int ncomp, int layout, int32_t* out) {
+  if (!c) PDE_FAIL("null context");
+  if (ncomp < 1 || ncomp > 3) PDE_FAIL("ncomp must be 1..3");
+  CUDA_OK(cudaSetDevice(c->device));
+  int64_t nv, nc;
+  PDE_OK(pde_mesh_counts(dim, n, &nv, &nc));
+  if (nv * ncomp > 2147483647LL) PDE_FAIL("dof indices exceed int32; export connectivity at smaller sizes only");
+  DevMem d;
+  size_t bytes = sizeof(int32_t) * nc * (dim + 1) * ncomp;
+  PDE_OK(d.alloc(bytes));
+  PDE_OK(launch_mesh_cells(c, dim, n, /*sorted=*/1, ncomp, layout, (int32_t*)d.p));
+  return d2h(c, out, d.p, bytes);
+}
+
+extern "C" int pde_mesh_cells(pde_ctx* c, int dim, const int32_t n[3], int sorted, int32_t* cells) {
+  if (!c) PDE_FAIL("null context");
+  CUDA_OK(cudaSetDevice(c->device));
+  int64_t nv, nc;
+  PDE_OK(pde_mesh_counts(dim, n, &nv, &nc));
+  if (nv > 2147483647LL) PDE_FAIL("vertex indices exceed int32");
+  DevMem d;
+  size_t bytes = sizeof(int32_t) * nc * (dim + 1);
+  PDE_OK(d.alloc(bytes));
+  PDE_OK(launch_mesh_cells(c, dim, n, sorted, 1, 0, (int32_t*)d.p));
+  return d2h(c, cells, d.p, bytes);
+}
+
+static int make_bc(int dim, const int32_t n[3], const pde_bc* bc, BcDev* out) {
+  user_bc_to_dev(dim, bc, out);
+  if (out->side_excl && n[0] < 3) {  // every side facet touches an x-end: the topological set is empty
+    for (int f = 2; f < 6; ++f) out->on[f] = 0;
+  }
+  return 0;
+}
+
+extern "C" int pde_boundary_mask(pde_ctx* c, int dim, const int32_t n[3], const pde_bc* bc, uint8_t* mask,
+                                 double* vals) {
+  if (!c) PDE_FAIL("null context");
+  CUDA_OK(cudaSetDevice(c->device));
+  const double L1[3] = {1, 1, 1};
+  Grid g;
+  PDE_OK(make_grid(dim, n, L1, 0, 1, &g));
+  BcDev b;
+  PDE_OK(make_bc(dim, n, bc, &b));
+  int64_t nv, nc;
+  PDE_OK(pde_mesh_counts(dim, n, &nv, &nc));
+  DevMem dm, dv;
+  PDE_OK(dm.alloc(nv));
+  PDE_OK(dv.alloc(sizeof(double) * nv));
+  PDE_OK(launch_bc_mask(c, g, b, (uint8_t*)dm.p, vals ? (double*)dv.p : nullptr));
+  PDE_OK(d2h(c, mask, dm.p, nv));
+  if (vals) PDE_OK(d2h(c, vals, dv.p, sizeof(double) * nv));
+  return 0;
+}
+
+// ---- heat ---------------------------------------------------------------------------------------
+struct pde_heat_state {
+  pde_ctx* c = nullptr;
+  pde_heat_params p{};
+  pde_solver_opts o{};
+  Grid g{};
+  BcDev bc{};
+  Operator A, K, M;
+  Hierarchy mg;
+  bool use_mg = false;
+  PcgWork w;
+  Field u, r;
+  DevMem dense;
+  long long nloc = 0;
+  long long steps_done = 0;
+  double setup_ms = 0;
+};
+
+extern "C" int pde_heat_close(pde_heat_state* s) {
+  if (!s) return 0;
+  cudaSetDevice(s->c->device);
+  cudaStreamSynchronize(s->c->stream);
+  s->A.release(); s->K.release(); s->M.release();
+  s->mg.release();
+  s->w.release();
+  s->u.release(); s->r.release();
+  delete s;
+  return 0;
+}
+
+extern "C" int pde_heat_open(pde_ctx* c, const pde_heat_params* p, const pde_solver_opts* o, pde_heat_state** out) {
+  if (!c || !p || !out) PDE_FAIL("null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  if (!p->steady && !(p->dt > 0)) PDE_FAIL("dt must be > 0");
+  if (!(p->diffusivity > 0)) PDE_FAIL("diffusivity must be > 0");
+  if (p->num_steps < 0) PDE_FAIL("num_steps must be >= 0");
+  if (p->initial_type == PDE_IC_COSINE || p->initial_type == PDE_IC_SINE)
+    PDE_FAIL("initial_type cosine/sine (consistent-mass projection of a P2-interpolated expression) "
+             "is not implemented in the CUDA path yet");
+  pde_heat_state* s = new (std::nothrow) pde_heat_state();
+  if (!s) PDE_FAIL("out of host memory");
+  s->c = c;
+  s->p = *p;
+  if (o) s->o = *o; else pde_solver_opts_default(&s->o);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, c->stream);
+  int rc = 0;
+  do {
+    if ((rc = make_grid(p->dim, p->n, p->L, c->rank, c->world, &s->g))) break;
+    if ((rc = make_bc(p->dim, p->n, &p->bc, &s->bc))) break;
+    const double kappa = p->diffusivity;
+    const double alpha = p->steady ? 0.0 : 1.0, beta = p->steady ? kappa : p->dt * kappa;
+    if ((rc = s->A.setup_scalar(c, s->g, s->bc, alpha, beta))) break;
+    if ((rc = s->K.setup_scalar(c, s->g, s->bc, 0.0, 1.0))) break;
+    if ((rc = s->M.setup_scalar(c, s->g, s->bc, 1.0, 0.0))) break;
+    if ((rc = s->u.alloc(s->g, 1))) break;
+    if ((rc = s->r.alloc(s->g, 1))) break;
+    if ((rc = s->w.alloc(s->g, 1))) break;
+    s->nloc = (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzl;
+    if ((rc = s->dense.alloc(sizeof(double) * s->nloc))) break;
+    long long ndofs = (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzg;
+    if (s->o.precond != PDE_PRECOND_JACOBI && c->world == 1) {
+      if ((rc = s->mg.build(c, s->A, PDE_OP_HEAT, alpha, beta))) break;
+      s->mg.nu = s->o.cheby_degree > 0 ? s->o.cheby_degree : 2;
+      s->mg.ratio = s->o.cheby_ratio > 1 ? s->o.cheby_ratio : 8.0;
+    }
+    s->use_mg = choose_precond(s->o, c, ndofs, s->mg) == PDE_PRECOND_GMG;
+    if (!s->use_mg) s->mg.release();
+    // initial condition (reference :276-297, 408-426, 672-691): fill, then bc.apply(u_n.vector())
+    double v0 = p->initial_type == PDE_IC_ZERO ? 0.0 : p->T_initial;
+    if (p->steady) v0 = 0.0;
+    if ((rc = launch_fill_ic(c, s->g, s->bc, s->u.p, v0, 1))) break;
+  } while (0);
+  cudaEventRecord(e1, c->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  s->setup_ms = ms;
+  if (rc) { pde_heat_close(s); return rc; }
+  *out = s;
+  return 0;
+}
+
+extern "C" int64_t pde_heat_local_nverts(pde_heat_state* s) { return s ? s->nloc : 0; }
+
+extern "C" int pde_heat_set_state(pde_heat_state* s, const double* u_host) {
+  if (!s || !u_host) PDE_FAIL("null argument");
+  pde_ctx* c = s->c;
+  CUDA_OK(cudaSetDevice(c->device));
+  CUDA_OK(cudaMemcpyAsync(s->dense.p, u_host, sizeof(double) * s->nloc, cudaMemcpyHostToDevice, c->stream));
+  PDE_OK(launch_unpack(c, s->g, 1, (const double*)s->dense.p, s->u.p, 0));
+  PDE_OK(launch_apply_bc_values(c, s->g, s->bc, s->u.p));
+  return 0;
+}
+
+extern "C" int pde_heat_get_state(pde_heat_state* s, double* u_host) {
+  if (!s || !u_host) PDE_FAIL("null argument");
+  pde_ctx* c = s->c;
+  CUDA_OK(cudaSetDevice(c->device));
+  PDE_OK(launch_pack(c, s->g, 1, s->u.p, (double*)s->dense.p, 0));
+  return d2h(c, u_host, s->dense.p, sizeof(double) * s->nloc);
+}
+
+static int heat_one_solve(pde_heat_state* s, pde_stats* st) {
+  pde_ctx* c = s->c;
+  const pde_heat_params& p = s->p;
+  const double f = p.source_value, kappa = p.diffusivity;
+  StencilArgs a;
+  a.x = s->u.p; a.y = s->r.p; a.bconst[0] = f; a.reduce_slot_xy = S_XY;
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, s->g, 1, s->u.p));
+  double bn2;
+  if (p.steady) {
+    // r0 = f m - kappa K u0 (u0 = Dirichlet lift): this IS the reduced right-hand side
+    a.bscale = 1.0; a.ascale = -1.0;
+    PDE_OK(launch_stencil(c, s->g, s->bc, s->A.dev, a));
+    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
+    PDE_OK(read_scal(c, S_YY, 1, &bn2));
+  } else {
+    // warm start x0 = u_n  =>  r0 = b - A u_n = dt (f m - kappa K u_n)   (b = M u_n + dt f m)
+    a.bscale = p.dt; a.ascale = -p.dt * kappa;
+    PDE_OK(launch_stencil(c, s->g, s->bc, s->K.dev, a));
+    StencilArgs nb;
+    nb.x = s->u.p; nb.y = nullptr; nb.bconst[0] = f; nb.bscale = p.dt; nb.ascale = 1.0; nb.reduce_slot_xy = S_XY;
+    PDE_OK(launch_stencil(c, s->g, s->bc, s->M.dev, nb));
+    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
+    PDE_OK(read_scal(c, S_YY, 1, &bn2));
+  }
+  return pcg_solve(c, s->A, s->use_mg ? &s->mg : nullptr, s->w, s->u.p, s->r.p, bn2, s->o, st);
+}
+
+static void stats_init(pde_stats* st, long long ndofs) {
+  std::memset(st, 0, sizeof(*st));
+  st->ndofs = ndofs;
+  st->converged = 1;
+  st->true_relres = NAN;
+}
+
+extern "C" int pde_heat_step(pde_heat_state* s, int nsteps, pde_stats* st_out) {
+  if (!s) PDE_FAIL("null state");
+  pde_ctx* c = s->c;
+  CUDA_OK(cudaSetDevice(c->device));
+  pde_stats st;
+  stats_init(&st, (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzg);
+  const long long l0 = c->launches;
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  for (int k = 0; k < nsteps; ++k) PDE_OK(heat_one_solve(s, &st));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  st.solve_ms = ms;
+  st.setup_ms = s->setup_ms;
+  st.launches = c->launches - l0;
+  s->steps_done += nsteps;
+  if (st_out) *st_out = st;
+  return 0;
+}
+
+extern "C" int pde_heat_solve(pde_ctx* c, const pde_heat_params* p, const pde_solver_opts* o, const double* u0,
+                              double* values_out, double* times_out, pde_stats* st_out) {
+  if (!values_out || !times_out) PDE_FAIL("null output buffers");
+  pde_heat_state* s = nullptr;
+  PDE_OK(pde_heat_open(c, p, o, &s));
+  int rc = 0;
+  pde_stats acc;
+  stats_init(&acc, (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzg);
+  do {
+    if (p->initial_type == PDE_IC_ARRAY) {
+      if (!u0) { pde_set_error("initial_type array needs u0"); rc = 1; break; }
+      if ((rc = pde_heat_set_state(s, u0))) break;
+    }
+    long long snap = 0;
+    if (p->steady) {
+      pde_stats st;
+      if ((rc = pde_heat_step(s, 1, &st))) break;
+      acc = st;
+      if ((rc = pde_heat_get_state(s, values_out))) break;
+      times_out[0] = 0.0;
+      break;
+    }
+    if ((rc = pde_heat_get_state(s, values_out))) break;
+    times_out[snap++] = 0.0;
+    const int stride = p->snapshot_stride > 0 ? p->snapshot_stride : 1;
+    for (int step = 0; step < p->num_steps; ++step) {
+      pde_stats st;
+      if ((rc = pde_heat_step(s, 1, &st))) break;
+      acc.iters_total += st.iters_total;
+      acc.solves += st.solves;
+      acc.converged &= st.converged;
+      acc.levels = st.levels;
+      acc.final_relres = st.final_relres;
+      acc.solve_ms += st.solve_ms;
+      acc.launches += st.launches;
+      if ((step + 1) % stride == 0) {
+        if ((rc = pde_heat_get_state(s, values_out + snap * s->nloc))) break;
+        times_out[snap++] = (step + 1) * p->dt;
+      }
+    }
+    acc.setup_ms = s->setup_ms;
+  } while (0);
+  pde_heat_close(s);
+  if (st_out) *st_out = acc;
+  return rc;
+}
+
+// ---- generic operator entry points -------------------------------------------------------------------
+static int setup_op(pde_ctx* c, const pde_op_params* p, Operator* A, int* ncomp) {
+  Grid g;
+  PDE_OK(make_grid(p->dim, p->n, p->L, c->rank, c->world, &g));
+  BcDev bc;
+  PDE_OK(make_bc(p->dim, p->n, &p->bc, &bc));
+  if (p->kind == PDE_OP_ELASTICITY) {
+    if (p->dim < 2) PDE_FAIL("elasticity operator needs dim 2 or 3");
+    PDE_OK(A->setup_elasticity(c, g, bc, p->lam, p->mu));
+  } else {
+    double a = p->kind == PDE_OP_MASS ? 1.0 : (p->kind == PDE_OP_STIFFNESS ? 0.0 : p->alpha);
+    double b = p->kind == PDE_OP_MASS ? 0.0 : (p->kind == PDE_OP_STIFFNESS ? 1.0 : p->beta);
+    PDE_OK(A->setup_scalar(c, g, bc, a, b));
+  }
+  *ncomp = A->tab.ncomp;
+  return 0;
+}
+
+struct OpGuard {
+  Operator A;
+  Field x, y, r;
+  PcgWork w;
+  Hierarchy mg;
+  ~OpGuard() { A.release(); x.release(); y.release(); r.release(); w.release(); mg.release(); }
+};
+
+extern "C" int pde_op_apply(pde_ctx* c, const pde_op_params* p, const double* x, double* y) {
+  if (!c || !p || !x || !y) PDE_FAIL("null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  OpGuard G;
+  int nc;
+  PDE_OK(setup_op(c, p, &G.A, &nc));
+  const Grid& g = G.A.g;
+  PDE_OK(G.x.alloc(g, nc));
+  PDE_OK(G.y.alloc(g, nc));
+  const long long nloc = (long long)g.nn[0] * g.nn[1] * g.nzl;
+  DevMem dense;
+  PDE_OK(dense.alloc(sizeof(double) * nloc * nc));
+  PDE_OK(h2d(c, dense.p, x, sizeof(double) * nloc * nc));
+  PDE_OK(launch_unpack(c, g, nc, (const double*)dense.p, G.x.p, 0));
+  StencilArgs a;
+  a.x = G.x.p; a.y = G.y.p; a.variant = p->variant; a.reduce_slot_xy = S_XY;
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, G.x.p));
+  PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  PDE_OK(launch_pack(c, g, nc, G.y.p, (double*)dense.p, 0));
+  return d2h(c, y, dense.p, sizeof(double) * nloc * nc);
+}
+
+__global__ void k_fill_pattern(const __grid_constant__ Grid g, int ncomp, double* __restrict__ x) {
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x)
+      for (int i = 0; i < ncomp; ++i) {
+        const long long node = row * g.nn[0] + ix;
+        x[(long long)g.PX * iy + g.plane * lz + ix + i * g.comp_stride] = sin(0.37 * (double)(node % 1000003) + i) + 0.5;
+      }
+  }
+}
+
+extern "C" int pde_op_bench(pde_ctx* c, const pde_op_params* p, int reps, int warmup, double* ms_per_apply,
+                            int64_t* ndofs) {
+  if (!c || !p) PDE_FAIL("null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  OpGuard G;
+  int nc;
+  PDE_OK(setup_op(c, p, &G.A, &nc));
+  const Grid& g = G.A.g;
+  PDE_OK(G.x.alloc(g, nc));
+  PDE_OK(G.y.alloc(g, nc));
+  RowLaunch rl = row_launch(c, g);
+  k_fill_pattern<<<rl.grid, rl.block, 0, c->stream>>>(g, nc, G.x.p);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  StencilArgs a;
+  a.x = G.x.p; a.y = G.y.p; a.variant = p->variant; a.reduce_slot_xy = S_XY;
+  for (int i = 0; i < warmup; ++i) PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < reps; ++i) PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (ms_per_apply) *ms_per_apply = ms / (reps > 0 ? reps : 1);
+  if (ndofs) *ndofs = (int64_t)g.nn[0] * g.nn[1] * g.nzl * nc;
+  return 0;
+}
+
+static int solve_with(pde_ctx* c, OpGuard& G, const pde_op_params* p, const pde_solver_opts& o, double* x, double* r,
+                      double bn2, pde_stats* st) {
+  const int nc = G.A.tab.ncomp;
+  long long ndofs = (long long)G.A.g.nn[0] * G.A.g.nn[1] * G.A.g.nzg * nc;
+  bool use_mg = false;
+  if (o.precond != PDE_PRECOND_JACOBI && c->world == 1) {
+    double p0 = p->kind == PDE_OP_ELASTICITY ? p->lam : (p->kind == PDE_OP_MASS ? 1.0 : (p->kind == PDE_OP_STIFFNESS ? 0.0 : p->alpha));
+    double p1 = p->kind == PDE_OP_ELASTICITY ? p->mu : (p->kind == PDE_OP_MASS ? 0.0 : (p->kind == PDE_OP_STIFFNESS ? 1.0 : p->beta));
+    PDE_OK(G.mg.build(c, G.A, p->kind == PDE_OP_ELASTICITY ? PDE_OP_ELASTICITY : PDE_OP_HEAT, p0, p1));
+    G.mg.nu = o.cheby_degree > 0 ? o.cheby_degree : 2;
+    G.mg.ratio = o.cheby_ratio > 1 ? o.cheby_ratio : 8.0;
+    use_mg = choose_precond(o, c, ndofs, G.mg) == PDE_PRECOND_GMG;
+  }
+  PDE_OK(G.w.alloc(G.A.g, nc));
+  return pcg_solve(c, G.A, use_mg ? &G.mg : nullptr, G.w, x, r, bn2, o, st);
+}
+
+extern "C" int pde_op_solve(pde_ctx* c, const pde_op_params* p, const pde_solver_opts* o_in, const double* b,
+                            double* x, pde_stats* st_out) {
+  if (!c || !p || !b || !x) PDE_FAIL("null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  pde_solver_opts o;
+  if (o_in) o = *o_in; else pde_solver_opts_default(&o);
+  OpGuard G;
+  int nc;
+  PDE_OK(setup_op(c, p, &G.A, &nc));
+  const Grid& g = G.A.g;
+  PDE_OK(G.x.alloc(g, nc));
+  PDE_OK(G.y.alloc(g, nc));  // holds b
+  PDE_OK(G.r.alloc(g, nc));
+  const long long nloc = (long long)g.nn[0] * g.nn[1] * g.nzl;
+  DevMem dense;
+  PDE_OK(dense.alloc(sizeof(double) * nloc * nc));
+  PDE_OK(h2d(c, dense.p, b, sizeof(double) * nloc * nc));
+  PDE_OK(launch_unpack(c, g, nc, (const double*)dense.p, G.y.p, 0));
+  for (int i = 0; i < nc; ++i) PDE_OK(launch_apply_bc_values(c, g, G.A.bc, G.x.p + i * g.comp_stride));
+  pde_stats st;
+  stats_init(&st, nloc * nc);
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  const long long l0 = c->launches;
+  StencilArgs a;
+  a.x = G.x.p; a.b = G.y.p; a.y = G.r.p; a.bscale = 1.0; a.ascale = -1.0; a.reduce_slot_xy = S_XY;
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, G.x.p));
+  PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
+  double bn2;
+  PDE_OK(read_scal(c, S_YY, 1, &bn2));
+  PDE_OK(solve_with(c, G, p, o, G.x.p, G.r.p, bn2, &st));
+  // true residual
+  a.x = G.x.p; a.y = nullptr;
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, G.x.p));
+  PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
+  double rr;
+  PDE_OK(read_scal(c, S_YY, 1, &rr));
+  st.true_relres = bn2 > 0 ? std::sqrt(rr / bn2) : 0.0;
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  st.solve_ms = ms;
+  st.launches = c->launches - l0;
+  PDE_OK(launch_pack(c, g, nc, G.x.p, (double*)dense.p, 0));
+  PDE_OK(d2h(c, x, dense.p, sizeof(double) * nloc * nc));
+  if (st_out) *st_out = st;
+  return 0;
+}
+
+// ---- elasticity -----------------------------------------------------------------------------------------
+extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const pde_solver_opts* o_in,
+                                    double* field_out, double* disp_out, pde_stats* st_out, pde_stats* st_proj_out) {
+  if (!c || !p || !field_out) PDE_FAIL("null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  if (c->world > 1) PDE_FAIL("pde_elasticity_solve: multi-GPU slabs are not wired for this entry point yet");
+  pde_solver_opts o;
+  if (o_in) o = *o_in; else pde_solver_opts_default(&o);
+  if (!(p->E > 0)) PDE_FAIL("E must be > 0");
+  const int dim = p->dim;
+  pde_bc ubc;
+  std::memset(&ubc, 0, sizeof(ubc));
+  ubc.face_on[0] = 1;  // clamp x = 0 (reference :1531-1534, 1681-1684, 1831-1834)
+  pde_op_params op;
+  std::memset(&op, 0, sizeof(op));
+  op.dim = dim;
+  for (int k = 0; k < 3; ++k) { op.n[k] = p->n[k]; op.L[k] = p->L[k]; }
+  op.bc = ubc;
+  double lam = 0, mu = 0;
+  if (dim == 1) {
+    op.kind = PDE_OP_HEAT; op.alpha = 0.0; op.beta = p->E * p->area;
+  } else {
+    if (!(p->nu > -1.0 && p->nu < 0.5)) PDE_FAIL("nu must be in (-1, 0.5)");
+    mu = p->E / (2.0 * (1.0 + p->nu));
+    lam = (dim == 2 && p->plane_stress) ? p->E * p->nu / (1.0 - p->nu * p->nu)
+                                        : p->E * p->nu / ((1.0 + p->nu) * (1.0 - 2.0 * p->nu));
+    op.kind = PDE_OP_ELASTICITY; op.lam = lam; op.mu = mu;
+  }
+  OpGuard G;
+  int nc;
+  PDE_OK(setup_op(c, &op, &G.A, &nc));
+  const Grid& g = G.A.g;
+  PDE_OK(G.x.alloc(g, nc));
+  PDE_OK(G.r.alloc(g, nc));
+  const long long nloc = (long long)g.nn[0] * g.nn[1] * g.nzl;
+  pde_stats st;
+  stats_init(&st, nloc * nc);
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  const long long l0 = c->launches;
+  // load vector b_{i,c} = f_c * integral(phi_i)  (L = dot(b, v) dx, :1528, 1678, 1828); x0 = 0 => r0 = b
+  StencilArgs a;
+  a.x = G.x.p; a.y = G.r.p; a.bscale = 1.0; a.ascale = -1.0; a.reduce_slot_xy = S_XY;
+  for (int i = 0; i < nc; ++i) a.bconst[i] = p->body[i];
+  PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  double bn2;
+  PDE_OK(read_scal(c, S_YY, 1, &bn2));
+  PDE_OK(solve_with(c, G, &op, o, G.x.p, G.r.p, bn2, &st));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  st.solve_ms = ms;
+  st.launches = c->launches - l0;
+  // projected scalar: M v = sum_cells value_c |c|/(d+1)   (project(eq_expr, Vs), :1541-1546, 1714, 1862)
+  SimplexGeom sg;
+  build_simplex_geom(dim, g.h, &sg);
+  OpGuard P;
+  pde_op_params mp = op;
+  mp.kind = PDE_OP_MASS;
+  std::memset(&mp.bc, 0, sizeof(mp.bc));
+  int nc1;
+  PDE_OK(setup_op(c, &mp, &P.A, &nc1));
+  PDE_OK(P.x.alloc(g, 1));
+  PDE_OK(P.r.alloc(g, 1));
+  pde_stats sp;
+  stats_init(&sp, nloc);
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  const long long l1 = c->launches;
+  const int mode = dim == 1 ? (p->quantity == 1 ? 2 : 3) : (p->quantity == 1 ? 1 : 0);
+  PDE_OK(launch_cell_rhs(c, g, nc, sg, G.x.p, P.r.p, mode, lam, mu, p->E));
+  PDE_OK(launch_dot(c, g, 1, P.r.p, P.r.p, S_TMP0));
+  double pn2;
+  PDE_OK(read_scal(c, S_TMP0, 1, &pn2));
+  pde_solver_opts po = o;
+  po.precond = PDE_PRECOND_JACOBI;   // consistent mass: kappa(D^-1 M) = O(10), Jacobi-PCG converges in ~20 its
+  po.rtol = o.rtol < 1e-12 ? o.rtol : 1e-12;
+  PDE_OK(solve_with(c, P, &mp, po, P.x.p, P.r.p, pn2, &sp));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  sp.solve_ms = ms;
+  sp.launches = c->launches - l1;
+  DevMem dense;
+  PDE_OK(dense.alloc(sizeof(double) * nloc * nc));
+  PDE_OK(launch_pack(c, g, 1, P.x.p, (double*)dense.p, 0));
+  PDE_OK(d2h(c, field_out, dense.p, sizeof(double) * nloc));
+  if (disp_out) {
+    PDE_OK(launch_pack(c, g, nc, G.x.p, (double*)dense.p, 1));
+    PDE_OK(d2h(c, disp_out, dense.p, sizeof(double) * nloc * nc));
+  }
+  if (st_out) *st_out = st;
+  if (st_proj_out) *st_proj_out = sp;
+  return 0;
+}

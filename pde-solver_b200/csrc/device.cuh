@@ -1,0 +1,150 @@
+// Device-side helpers and the execution context shared by kernels.cu / solver.cu / cabi.cu.
+#pragma once
+#include "common.h"
+
+#define RED_MAX_BLOCKS 4096
+#define RED_MAX_VALS 4
+
+// scalar slots (device doubles) used by the PCG recurrences
+enum { S_RHO0 = 0, S_RHO1 = 1, S_PAP = 2, S_RR = 3, S_XY = 4, S_YY = 5, S_TMP0 = 6, S_TMP1 = 7, S_NSLOTS = 16 };
+
+struct ReduceBuf {
+  double* partials;   // [RED_MAX_BLOCKS][RED_MAX_VALS]
+  unsigned* counter;  // zero between kernels
+};
+
+struct NcclApi;  // comm.cu
+
+struct pde_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
+  ReduceBuf red{};
+  double* scal = nullptr;     // device [S_NSLOTS]
+  double* h_scal = nullptr;   // pinned host mirror [S_NSLOTS]
+  long long launches = 0;
+  // multi-GPU
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+  NcclApi* nccl = nullptr;
+};
+
+// ---- geometry helpers -----------------------------------------------------------------
+__host__ __device__ __forceinline__ int axis_class(int i, int n) {
+  return n == 1 ? 1 : (i == 0 ? 0 : (i == n - 1 ? 2 : 1));
+}
+__host__ __device__ __forceinline__ int node_class(const Grid& g, int ix, int iy, int gz) {
+  return axis_class(ix, g.nn[0]) + 3 * axis_class(iy, g.nn[1]) + 9 * axis_class(gz, g.nzg);
+}
+// Topological DirichletBC of the reference restated on lattice indices:
+// x faces first (left/right), then the remaining faces; "other_faces" skips the x-end columns.
+__host__ __device__ __forceinline__ bool bc_node(const Grid& g, const BcDev& bc, int ix, int iy, int gz,
+                                                 double* val) {
+  const bool x0 = g.nc[0] > 0 && ix == 0, x1 = g.nc[0] > 0 && ix == g.nn[0] - 1;
+  if (x0 && bc.on[0]) { *val = bc.val[0]; return true; }
+  if (x1 && bc.on[1]) { *val = bc.val[1]; return true; }
+  if (bc.side_excl && (x0 || x1)) return false;
+  if (g.nc[1] > 0) {
+    if (iy == 0 && bc.on[2]) { *val = bc.val[2]; return true; }
+    if (iy == g.nn[1] - 1 && bc.on[3]) { *val = bc.val[3]; return true; }
+  }
+  if (g.nc[2] > 0) {
+    if (gz == 0 && bc.on[4]) { *val = bc.val[4]; return true; }
+    if (gz == g.nzg - 1 && bc.on[5]) { *val = bc.val[5]; return true; }
+  }
+  return false;
+}
+
+// flat offset of Kuhn-stencil neighbour k (folds to a constant after unrolling)
+__device__ __forceinline__ long long kOffDdev(int k, int PX, long long plane) {
+  constexpr int D[PDE_NOFF][3] = {{0, 0, 0},  {1, 0, 0},  {-1, 0, 0},  {0, 1, 0},  {0, -1, 0},
+                                  {0, 0, 1},  {0, 0, -1}, {1, 1, 0},   {-1, -1, 0}, {1, 0, 1},
+                                  {-1, 0, -1}, {0, 1, 1}, {0, -1, -1}, {1, 1, 1},   {-1, -1, -1}};
+  return D[k][0] + (long long)PX * D[k][1] + plane * D[k][2];
+}
+
+// ---- launch geometry for row-structured kernels -----------------------------------------
+struct RowLaunch {
+  dim3 block, grid;
+};
+static inline RowLaunch row_launch(const pde_ctx* c, const Grid& g) {
+  RowLaunch r;
+  int bx = g.nn[0] >= 96 ? 128 : (g.nn[0] > 32 ? 64 : 32);
+  int by = 128 / bx;
+  long long rows = (long long)g.nn[1] * g.nzl;
+  long long blocks = (rows + by - 1) / by;
+  long long cap = (long long)c->sm_count * 16;
+  if (cap > RED_MAX_BLOCKS) cap = RED_MAX_BLOCKS;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  r.block = dim3(bx, by, 1);
+  r.grid = dim3((unsigned)blocks, 1, 1);
+  return r;
+}
+static inline int flat_blocks(const pde_ctx* c, long long n_items, int threads) {
+  long long blocks = (n_items + threads - 1) / threads;
+  long long cap = (long long)c->sm_count * 8;
+  if (cap > RED_MAX_BLOCKS) cap = RED_MAX_BLOCKS;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---- kernels.cu API (all asynchronous on ctx->stream) ------------------------------------
+struct OpDev {
+  int ncomp = 1;
+  double* coef = nullptr;   // [27][15][nc*nc]
+  double* dinv = nullptr;   // [27][nc]
+  double* load = nullptr;   // [27]
+  double h_int[PDE_NOFF * 9];  // interior class coefficients (host copy, passed as kernel params)
+  double gershgorin = 0;
+};
+
+struct StencilArgs {
+  const double* x = nullptr;   // input field (ghost/pad zero)
+  const double* b = nullptr;   // optional right-hand side field; if null, B_i = bconst[c]*load[class]
+  double* y = nullptr;         // output (may be null: reductions only)
+  double* d = nullptr;         // Chebyshev direction (cheby mode)
+  double bconst[3] = {0, 0, 0};
+  double bscale = 0, ascale = 1;  // y = bscale*B + ascale*(A x)
+  double c1 = 0, c2 = 0;          // cheby: d = c1*d + c2*dinv*(B - A x); y = x + d
+  int cheby = 0;
+  int reduce_slot_xy = -1;        // scal slot receiving sum x.y (and +1: sum y.y) ; -1: none
+  int variant = 0;
+};
+
+int launch_stencil(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
+// Jacobi-PCG fused update: x += a p, r -= a q, rho_new = r.dinv r, rr = r.r  (a = rho/pAp from scal)
+int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, double* r, const double* p,
+                     const double* q, int slot_rho, int slot_pap, int slot_rho_new, int slot_rr, int jacobi);
+// p = z + beta p with z = dinv r (jacobi) or z given; beta = rho_new/rho (first: beta = 0)
+int launch_cg_pupdate(pde_ctx* c, const Grid& g, const OpDev& op, double* p, const double* r_or_z,
+                      int slot_rho, int slot_rho_new, int first, int jacobi);
+int launch_dot(pde_ctx* c, const Grid& g, int ncomp, const double* a, const double* b, int slot);
+int launch_zero(pde_ctx* c, const Grid& g, int ncomp, double* a);
+int launch_copy(pde_ctx* c, const Grid& g, int ncomp, double* dst, const double* src);
+int launch_axpy(pde_ctx* c, const Grid& g, int ncomp, double* y, const double* x, double alpha);
+// first Chebyshev sweep from a zero guess: d = s*dinv*b ; x = d
+int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* b, double* d,
+                       double* x, double s);
+int launch_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcc, int ncomp, const double* rf,
+                    double* bcoarse);
+int launch_prolong_add(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcf, int ncomp, const double* xc,
+                       double* xf);
+// fields
+int launch_fill_ic(pde_ctx* c, const Grid& g, const BcDev& bc, double* u, double value, int apply_bc);
+int launch_apply_bc_values(pde_ctx* c, const Grid& g, const BcDev& bc, double* u);
+int launch_pack(pde_ctx* c, const Grid& g, int ncomp, const double* padded, double* dense, int interleave);
+int launch_unpack(pde_ctx* c, const Grid& g, int ncomp, const double* dense, double* padded, int interleave);
+int launch_cell_rhs(pde_ctx* c, const Grid& g, int ncomp, const SimplexGeom& sg, const double* u, double* rhs,
+                    int mode, double lam, double mu, double Emod);
+int launch_dense_solve(pde_ctx* c, int n, const double* Ainv, const long long* idx, const double* b, double* x);
+// mesh
+int launch_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* out);
+int launch_mesh_cells(pde_ctx* c, int dim, const int32_t n[3], int sorted, int ncomp, int layout, int32_t* out);
+int launch_bc_mask(pde_ctx* c, const Grid& g, const BcDev& bc, uint8_t* mask, double* vals);
+
+// comm.cu
+int comm_allreduce_scal(pde_ctx* c, int slot, int count);
+int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* field);

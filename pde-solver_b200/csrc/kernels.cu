@@ -1,0 +1,797 @@
+// Generic (table-driven) sm_100a kernels: correct for every node class, dimension and BC set.
+// The specialised streaming kernels for the 3D hot paths live in stencil3d.cu.
+//
+// Replaces, matrix-free, what the reference does through DOLFIN assembly + PETSc LU:
+//   k_stencil        : y = bs*B + as*(A x)  /  Chebyshev sweep   (forms fenics_mcp_server.py:261-262,
+//                      304-305, 393-394, 433-434, 657-658, 702-703, 1527-1528, 1677-1678, 1827-1828)
+//   k_cg_*           : the linear solve of solve(a == L, u, bcs)  (:311, 440, 709, 1538, 1688, 1838)
+//   k_cell_rhs       : von-Mises / axial stress-strain load of project(eq_expr, Vs) (:1541-1546,
+//                      1691-1714, 1841-1862)
+//   k_mesh_*         : IntervalMesh/RectangleMesh/BoxMesh + P1 dof maps (:229-230, 369-370, 533-535)
+#include "device.cuh"
+
+// ----------------------------------------------------------------------------------------------
+// deterministic two-stage reduction: per-block partials, last block sums them in fixed order
+// ----------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], ReduceBuf red, double* out) {
+  __shared__ double sm[NV][32];
+  __shared__ bool is_last;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nth = blockDim.x * blockDim.y;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = (nth + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) sm[i][warp] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = lane < nwarp ? sm[i][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) red.partials[(size_t)blockIdx.x * RED_MAX_VALS + i] = s;
+    }
+    if (lane == 0) {
+      __threadfence();
+      unsigned t = atomicAdd(red.counter, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = 0.0;
+    for (unsigned b = tid; b < gridDim.x; b += nth) s += red.partials[(size_t)b * RED_MAX_VALS + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if (lane == 0) sm[i][warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double t = lane < nwarp ? sm[i][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      if (lane == 0) out[i] = t;
+    }
+  }
+  if (tid == 0) *red.counter = 0u;
+}
+
+// ----------------------------------------------------------------------------------------------
+// generic stencil kernel
+// ----------------------------------------------------------------------------------------------
+template <int NC>
+struct IntCoef {
+  double c[PDE_NOFF][NC * NC];
+};
+
+struct StencilDev {
+  const double* x;
+  const double* b;
+  double* y;
+  double* d;
+  double bconst[3];
+  double bscale, ascale, c1, c2;
+  int do_reduce;
+};
+
+template <int NC, bool CHEBY>
+__global__ void __launch_bounds__(128)
+k_stencil(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
+          const __grid_constant__ IntCoef<NC> ic, const double* __restrict__ coef,
+          const double* __restrict__ dinv, const double* __restrict__ load,
+          const __grid_constant__ StencilDev a, ReduceBuf red, double* red_out) {
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  double acc_xy = 0.0, acc_yy = 0.0;
+  const bool fast3d = (g.nk == PDE_NOFF);
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    const int gz = lz + g.z0;
+    const long long rbase = (long long)g.PX * iy + g.plane * lz;
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      const long long idx = rbase + ix;
+      double bcv;
+      const bool isdir = bc_node(g, bc, ix, iy, gz, &bcv);
+      if (isdir) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          if (CHEBY) {
+            a.d[idx + i * g.comp_stride] = 0.0;
+            a.y[idx + i * g.comp_stride] = a.x[idx + i * g.comp_stride];
+          } else if (a.y) {
+            a.y[idx + i * g.comp_stride] = 0.0;
+          }
+        }
+        continue;
+      }
+      const int cls = node_class(g, ix, iy, gz);
+      double acc[NC];
+#pragma unroll
+      for (int i = 0; i < NC; ++i) acc[i] = 0.0;
+      if (fast3d && cls == 13) {
+#pragma unroll
+        for (int k = 0; k < PDE_NOFF; ++k) {
+          const long long off = kOffDdev(k, g.PX, g.plane);
+          double xv[NC];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) xv[j] = a.x[idx + off + j * g.comp_stride];
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[i] = fma(ic.c[k][i * NC + j], xv[j], acc[i]);
+        }
+      } else {
+        for (int k = 0; k < g.nk; ++k) {
+          const double* cf = coef + ((size_t)cls * PDE_NOFF + g.kidx[k]) * (NC * NC);
+          const long long off = g.koff[k];
+          double xv[NC];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) xv[j] = a.x[idx + off + j * g.comp_stride];
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[i] = fma(__ldg(cf + i * NC + j), xv[j], acc[i]);
+        }
+      }
+      const double ld = a.b ? 0.0 : __ldg(load + cls);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const long long ii = idx + i * g.comp_stride;
+        const double B = a.b ? a.b[ii] : a.bconst[i] * ld;
+        if (CHEBY) {
+          const double r = B - acc[i];
+          const double dn = a.c1 * a.d[ii] + a.c2 * __ldg(dinv + cls * NC + i) * r;
+          a.d[ii] = dn;
+          a.y[ii] = a.x[ii] + dn;
+        } else {
+          const double yv = a.bscale * B + a.ascale * acc[i];
+          if (a.y) a.y[ii] = yv;
+          if (a.do_reduce) {
+            acc_xy = fma(a.x[ii], yv, acc_xy);
+            acc_yy = fma(yv, yv, acc_yy);
+          }
+        }
+      }
+    }
+  }
+  if (!CHEBY && a.do_reduce) {
+    double v[2] = {acc_xy, acc_yy};
+    block_reduce_finalize<2>(v, red, red_out);
+  }
+}
+
+template <int NC>
+static int launch_stencil_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
+  IntCoef<NC> ic;
+  for (int k = 0; k < PDE_NOFF; ++k)
+    for (int q = 0; q < NC * NC; ++q) ic.c[k][q] = op.h_int[k * NC * NC + q];
+  StencilDev sd;
+  sd.x = a.x; sd.b = a.b; sd.y = a.y; sd.d = a.d;
+  for (int i = 0; i < 3; ++i) sd.bconst[i] = a.bconst[i];
+  sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2;
+  sd.do_reduce = a.reduce_slot_xy >= 0;
+  RowLaunch rl = row_launch(c, g);
+  double* out = sd.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
+  if (a.cheby)
+    k_stencil<NC, true><<<rl.grid, rl.block, 0, c->stream>>>(g, bc, ic, op.coef, op.dinv, op.load, sd, c->red, out);
+  else
+    k_stencil<NC, false><<<rl.grid, rl.block, 0, c->stream>>>(g, bc, ic, op.coef, op.dinv, op.load, sd, c->red, out);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_stencil_generic(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
+  switch (op.ncomp) {
+    case 1: return launch_stencil_t<1>(c, g, bc, op, a);
+    case 2: return launch_stencil_t<2>(c, g, bc, op, a);
+    case 3: return launch_stencil_t<3>(c, g, bc, op, a);
+  }
+  PDE_FAIL("unsupported component count");
+}
+
+// ----------------------------------------------------------------------------------------------
+// PCG vector kernels (row-structured: the Jacobi diagonal depends on the node class)
+// ----------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(128)
+k_cg_update(const __grid_constant__ Grid g, const double* __restrict__ dinv, double* __restrict__ x,
+            double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q,
+            const double* __restrict__ scal, int s_rho, int s_pap, ReduceBuf red, double* out_rho_new,
+            double* out_rr) {
+  const double pap = scal[s_pap], rho = scal[s_rho];
+  const double alpha = pap > 0.0 ? rho / pap : 0.0;
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  double rz = 0.0, rr = 0.0;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    const long long rbase = (long long)g.PX * iy + g.plane * lz;
+    const int cyz = 3 * axis_class(iy, g.nn[1]) + 9 * axis_class(lz + g.z0, g.nzg);
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      const int cls = axis_class(ix, g.nn[0]) + cyz;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const long long ii = rbase + ix + i * g.comp_stride;
+        const double pv = p[ii], qv = q[ii];
+        x[ii] = fma(alpha, pv, x[ii]);
+        const double rv = fma(-alpha, qv, r[ii]);
+        r[ii] = rv;
+        rr = fma(rv, rv, rr);
+        rz = fma(rv * __ldg(dinv + cls * NC + i), rv, rz);
+      }
+    }
+  }
+  double v[2] = {rz, rr};
+  // the caller guarantees out_rr == out_rho_new + 1: one finalize writes both sums
+  block_reduce_finalize<2>(v, red, out_rho_new);
+  (void)out_rr;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(128)
+k_cg_pupdate(const __grid_constant__ Grid g, const double* __restrict__ dinv, double* __restrict__ p,
+             const double* __restrict__ rz, const double* __restrict__ scal, int s_rho, int s_rho_new,
+             int first, int jacobi) {
+  double beta = 0.0;
+  if (!first) {
+    const double rho = scal[s_rho];
+    beta = rho > 0.0 ? scal[s_rho_new] / rho : 0.0;
+  }
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    const long long rbase = (long long)g.PX * iy + g.plane * lz;
+    const int cyz = 3 * axis_class(iy, g.nn[1]) + 9 * axis_class(lz + g.z0, g.nzg);
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      const int cls = axis_class(ix, g.nn[0]) + cyz;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const long long ii = rbase + ix + i * g.comp_stride;
+        const double z = jacobi ? rz[ii] * __ldg(dinv + cls * NC + i) : rz[ii];
+        p[ii] = first ? z : fma(beta, p[ii], z);
+      }
+    }
+  }
+}
+
+#define DISPATCH_NC(nc, CALL)                       \
+  switch (nc) {                                     \
+    case 1: { constexpr int NC = 1; CALL; } break;  \
+    case 2: { constexpr int NC = 2; CALL; } break;  \
+    case 3: { constexpr int NC = 3; CALL; } break;  \
+    default: PDE_FAIL("unsupported component count"); \
+  }
+
+int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, double* r, const double* p,
+                     const double* q, int slot_rho, int slot_pap, int slot_rho_new, int slot_rr, int jacobi) {
+  (void)jacobi;
+  if (slot_rr != slot_rho_new + 1) PDE_FAIL("cg_update needs adjacent (rho_new, rr) slots");
+  RowLaunch rl = row_launch(c, g);
+  DISPATCH_NC(op.ncomp, (k_cg_update<NC><<<rl.grid, rl.block, 0, c->stream>>>(
+                            g, op.dinv, x, r, p, q, c->scal, slot_rho, slot_pap, c->red, c->scal + slot_rho_new,
+                            c->scal + slot_rr)));
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_cg_pupdate(pde_ctx* c, const Grid& g, const OpDev& op, double* p, const double* r_or_z, int slot_rho,
+                      int slot_rho_new, int first, int jacobi) {
+  RowLaunch rl = row_launch(c, g);
+  DISPATCH_NC(op.ncomp, (k_cg_pupdate<NC><<<rl.grid, rl.block, 0, c->stream>>>(
+                            g, op.dinv, p, r_or_z, c->scal, slot_rho, slot_rho_new, first, jacobi)));
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// flat vector kernels over the padded range (pads are zero and stay zero)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_dot(const double* __restrict__ a, const double* __restrict__ b, long long n, int ncomp, long long cs,
+      ReduceBuf red, double* out) {
+  double s = 0.0;
+  const long long n2 = n >> 1;
+  for (int cidx = 0; cidx < ncomp; ++cidx) {
+    const double2* a2 = reinterpret_cast<const double2*>(a + cidx * cs);
+    const double2* b2 = reinterpret_cast<const double2*>(b + cidx * cs);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+      const double2 u = a2[i], w = b2[i];
+      s = fma(u.x, w.x, s);
+      s = fma(u.y, w.y, s);
+    }
+  }
+  double v[1] = {s};
+  block_reduce_finalize<1>(v, red, out);
+}
+
+__global__ void __launch_bounds__(256)
+k_axpy(double* __restrict__ y, const double* __restrict__ x, double alpha, long long n, int ncomp, long long cs,
+       int mode) {
+  const long long n2 = n >> 1;
+  for (int cidx = 0; cidx < ncomp; ++cidx) {
+    double2* y2 = reinterpret_cast<double2*>(y + cidx * cs);
+    const double2* x2 = reinterpret_cast<const double2*>(x + cidx * cs);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+      if (mode == 0) {  // y += alpha x
+        double2 u = y2[i];
+        const double2 w = x2[i];
+        u.x = fma(alpha, w.x, u.x);
+        u.y = fma(alpha, w.y, u.y);
+        y2[i] = u;
+      } else if (mode == 1) {  // y = x
+        y2[i] = x2[i];
+      } else {  // y = 0
+        y2[i] = make_double2(0.0, 0.0);
+      }
+    }
+  }
+}
+
+int launch_dot(pde_ctx* c, const Grid& g, int ncomp, const double* a, const double* b, int slot) {
+  int blocks = flat_blocks(c, g.total / 2, 256 * 4);
+  k_dot<<<blocks, 256, 0, c->stream>>>(a, b, g.total, ncomp, g.comp_stride, c->red, c->scal + slot);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int launch_axpy_mode(pde_ctx* c, const Grid& g, int ncomp, double* y, const double* x, double alpha, int mode) {
+  int blocks = flat_blocks(c, g.total / 2, 256 * 4);
+  k_axpy<<<blocks, 256, 0, c->stream>>>(y, x, alpha, g.total, ncomp, g.comp_stride, mode);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_zero(pde_ctx* c, const Grid& g, int ncomp, double* a) { return launch_axpy_mode(c, g, ncomp, a, a, 0.0, 2); }
+int launch_copy(pde_ctx* c, const Grid& g, int ncomp, double* dst, const double* src) {
+  return launch_axpy_mode(c, g, ncomp, dst, src, 0.0, 1);
+}
+int launch_axpy(pde_ctx* c, const Grid& g, int ncomp, double* y, const double* x, double alpha) {
+  return launch_axpy_mode(c, g, ncomp, y, x, alpha, 0);
+}
+
+// ----------------------------------------------------------------------------------------------
+// multigrid transfer + first Chebyshev sweep
+// ----------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(128)
+k_cheby_first(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, const double* __restrict__ dinv,
+              const double* __restrict__ b, double* __restrict__ d, double* __restrict__ x, double s) {
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    const int gz = lz + g.z0;
+    const long long rbase = (long long)g.PX * iy + g.plane * lz;
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      double bcv;
+      const bool isdir = bc_node(g, bc, ix, iy, gz, &bcv);
+      const int cls = node_class(g, ix, iy, gz);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const long long ii = rbase + ix + i * g.comp_stride;
+        const double v = isdir ? 0.0 : s * __ldg(dinv + cls * NC + i) * b[ii];
+        d[ii] = v;
+        x[ii] = v;
+      }
+    }
+  }
+}
+
+int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* b, double* d,
+                       double* x, double s) {
+  RowLaunch rl = row_launch(c, g);
+  DISPATCH_NC(op.ncomp, (k_cheby_first<NC><<<rl.grid, rl.block, 0, c->stream>>>(g, bc, op.dinv, b, d, x, s)));
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// R = P^T : coarse node C gathers r_f(2C) + 1/2 sum over the 14 (6, 2) Kuhn edge directions
+template <int NC>
+__global__ void __launch_bounds__(128)
+k_restrict(const __grid_constant__ Grid gf, const __grid_constant__ Grid gc, const __grid_constant__ BcDev bcc,
+           const double* __restrict__ rf, double* __restrict__ bc_out) {
+  const long long rows = (long long)gc.nn[1] * gc.nzl;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % gc.nn[1]);
+    const int lz = (int)(row / gc.nn[1]);
+    const int gz = lz + gc.z0;
+    const long long cbase = (long long)gc.PX * iy + gc.plane * lz;
+    const int fy = gf.nc[1] > 0 ? 2 * iy : 0;
+    const int flz = (gf.nc[2] > 0 ? 2 * gz : 0) - gf.z0;
+    const long long fbase = (long long)gf.PX * fy + gf.plane * flz;
+    for (int ix = threadIdx.x; ix < gc.nn[0]; ix += blockDim.x) {
+      double bcv;
+      const bool isdir = bc_node(gc, bcc, ix, iy, gz, &bcv);
+      const long long fi = fbase + 2 * ix;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        double s = 0.0;
+        if (!isdir) {
+          const double* rp = rf + i * gf.comp_stride;
+          double nb = 0.0;
+          for (int k = 1; k < gf.nk; ++k) nb += rp[fi + gf.koff[k]];
+          s = rp[fi] + 0.5 * nb;
+        }
+        bc_out[cbase + ix + i * gc.comp_stride] = s;
+      }
+    }
+  }
+}
+
+int launch_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcc, int ncomp, const double* rf,
+                    double* bcoarse) {
+  RowLaunch rl = row_launch(c, gc);
+  DISPATCH_NC(ncomp, (k_restrict<NC><<<rl.grid, rl.block, 0, c->stream>>>(gf, gc, bcc, rf, bcoarse)));
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// x_f += P x_c : fine node with parity pi is the midpoint of the coarse Kuhn edge ((f-pi)/2,(f+pi)/2)
+template <int NC>
+__global__ void __launch_bounds__(128)
+k_prolong_add(const __grid_constant__ Grid gf, const __grid_constant__ Grid gc, const __grid_constant__ BcDev bcf,
+              const double* __restrict__ xc, double* __restrict__ xf) {
+  const long long rows = (long long)gf.nn[1] * gf.nzl;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % gf.nn[1]);
+    const int lz = (int)(row / gf.nn[1]);
+    const int gz = lz + gf.z0;
+    const long long fbase = (long long)gf.PX * iy + gf.plane * lz;
+    const int py = gf.nc[1] > 0 ? (iy & 1) : 0;
+    const int pz = gf.nc[2] > 0 ? (gz & 1) : 0;
+    const int cy = gf.nc[1] > 0 ? (iy - py) / 2 : 0;
+    const int clz = (gf.nc[2] > 0 ? (gz - pz) / 2 : 0) - gc.z0;
+    const long long cbase = (long long)gc.PX * cy + gc.plane * clz;
+    const long long cpy = (long long)gc.PX * py + gc.plane * pz;
+    for (int ix = threadIdx.x; ix < gf.nn[0]; ix += blockDim.x) {
+      double bcv;
+      if (bc_node(gf, bcf, ix, iy, gz, &bcv)) continue;
+      const int px = ix & 1;
+      const long long lo = cbase + (ix - px) / 2;
+      const long long hi = lo + px + cpy;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const double* cp = xc + i * gc.comp_stride;
+        xf[fbase + ix + i * gf.comp_stride] += 0.5 * (cp[lo] + cp[hi]);
+      }
+    }
+  }
+}
+
+int launch_prolong_add(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcf, int ncomp, const double* xc,
+                       double* xf) {
+  RowLaunch rl = row_launch(c, gf);
+  DISPATCH_NC(ncomp, (k_prolong_add<NC><<<rl.grid, rl.block, 0, c->stream>>>(gf, gc, bcf, xc, xf)));
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// coarsest level: x = A^-1 b on the free dofs, one warp per row of the precomputed dense inverse
+__global__ void __launch_bounds__(256)
+k_dense_solve(int n, const double* __restrict__ Ainv, const long long* __restrict__ idx, const double* __restrict__ b,
+              double* __restrict__ x) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) s = fma(Ainv[(size_t)warp * n + j], b[idx[j]], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) x[idx[warp]] = s;
+}
+
+int launch_dense_solve(pde_ctx* c, int n, const double* Ainv, const long long* idx, const double* b, double* x) {
+  if (n <= 0) return 0;
+  int blocks = (n * 32 + 255) / 256;
+  k_dense_solve<<<blocks, 256, 0, c->stream>>>(n, Ainv, idx, b, x);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// fields: initial condition / BC values / dense <-> padded layout
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_fill_ic(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, double* __restrict__ u, double value,
+          int fill, int apply_bc) {
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    const long long rbase = (long long)g.PX * iy + g.plane * lz;
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      double bcv;
+      const bool isdir = apply_bc && bc_node(g, bc, ix, iy, lz + g.z0, &bcv);
+      if (isdir) u[rbase + ix] = bcv;
+      else if (fill) u[rbase + ix] = value;
+    }
+  }
+}
+int launch_fill_ic(pde_ctx* c, const Grid& g, const BcDev& bc, double* u, double value, int apply_bc) {
+  RowLaunch rl = row_launch(c, g);
+  k_fill_ic<<<rl.grid, rl.block, 0, c->stream>>>(g, bc, u, value, 1, apply_bc);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_apply_bc_values(pde_ctx* c, const Grid& g, const BcDev& bc, double* u) {
+  RowLaunch rl = row_launch(c, g);
+  k_fill_ic<<<rl.grid, rl.block, 0, c->stream>>>(g, bc, u, 0.0, 0, 1);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// dense = natural lattice order of the local planes; interleave: dense[node*nc+c] else dense[c*nloc+node]
+template <bool PACK>
+__global__ void __launch_bounds__(128)
+k_pack(const __grid_constant__ Grid g, int ncomp, double* __restrict__ padded, double* __restrict__ dense,
+       int interleave) {
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  const long long nloc = (long long)g.nn[0] * rows;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    const long long rbase = (long long)g.PX * iy + g.plane * lz;
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      const long long node = row * g.nn[0] + ix;
+      for (int i = 0; i < ncomp; ++i) {
+        const long long di = interleave ? node * ncomp + i : i * nloc + node;
+        if (PACK) dense[di] = padded[rbase + ix + i * g.comp_stride];
+        else padded[rbase + ix + i * g.comp_stride] = dense[di];
+      }
+    }
+  }
+}
+int launch_pack(pde_ctx* c, const Grid& g, int ncomp, const double* padded, double* dense, int interleave) {
+  RowLaunch rl = row_launch(c, g);
+  k_pack<true><<<rl.grid, rl.block, 0, c->stream>>>(g, ncomp, const_cast<double*>(padded), dense, interleave);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_unpack(pde_ctx* c, const Grid& g, int ncomp, const double* dense, double* padded, int interleave) {
+  RowLaunch rl = row_launch(c, g);
+  k_pack<false><<<rl.grid, rl.block, 0, c->stream>>>(g, ncomp, padded, const_cast<double*>(dense), interleave);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// load vector of project(eq_expr, Vs): b_i = sum over incident simplices of value_simplex*|simplex|/(d+1)
+// gather form (no atomics, deterministic).  mode 0: von-Mises stress, 1: von-Mises strain,
+// 2: axial strain du/dx, 3: axial stress E du/dx (1D bar).
+// ----------------------------------------------------------------------------------------------
+template <int NC>
+__global__ void __launch_bounds__(128)
+k_cell_rhs(const __grid_constant__ Grid g, const __grid_constant__ SimplexGeom sg, const double* __restrict__ u,
+           double* __restrict__ rhs, int mode, double lam, double mu, double Emod) {
+  // component i <-> internal axis axm[i]
+  const int axm[3] = {0, g.dim == 2 ? 2 : 1, 2};
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  const double w = sg.vol / (double)(g.dim + 1);
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    const int gz = lz + g.z0;
+    const long long rbase = (long long)g.PX * iy + g.plane * lz;
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      const long long idx = rbase + ix;
+      double acc = 0.0;
+      for (int o = 0; o < 8; ++o) {
+        const int ox = o & 1, oy = (o >> 1) & 1, oz = (o >> 2) & 1;
+        if ((ox && (g.nc[0] == 0 || ix == 0)) || (!ox && g.nc[0] > 0 && ix == g.nn[0] - 1)) continue;
+        if ((oy && (g.nc[1] == 0 || iy == 0)) || (!oy && g.nc[1] > 0 && iy == g.nn[1] - 1)) continue;
+        if ((oz && (g.nc[2] == 0 || gz == 0)) || (!oz && g.nc[2] > 0 && gz == g.nzg - 1)) continue;
+        const long long cell0 = idx - ox - (long long)g.PX * oy - g.plane * oz;  // corner 0 of the cell
+        for (int t = 0; t < sg.nsimp; ++t) {
+          bool has = false;
+          for (int a = 0; a < sg.nv; ++a) has |= (sg.corner[t][a] == o);
+          if (!has) continue;
+          double gu[NC][3];
+#pragma unroll
+          for (int i = 0; i < NC; ++i) gu[i][0] = gu[i][1] = gu[i][2] = 0.0;
+          for (int a = 0; a < sg.nv; ++a) {
+            const int cb = sg.corner[t][a];
+            const long long vi = cell0 + (cb & 1) + (long long)g.PX * ((cb >> 1) & 1) + g.plane * ((cb >> 2) & 1);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+              const double uv = u[vi + i * g.comp_stride];
+              gu[i][0] = fma(uv, sg.G[t][a][0], gu[i][0]);
+              gu[i][1] = fma(uv, sg.G[t][a][1], gu[i][1]);
+              gu[i][2] = fma(uv, sg.G[t][a][2], gu[i][2]);
+            }
+          }
+          double val;
+          if (mode >= 2) {
+            val = gu[0][0] * (mode == 3 ? Emod : 1.0);
+          } else {
+            double eps[NC][NC];
+            double tr = 0.0;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+#pragma unroll
+              for (int j = 0; j < NC; ++j) eps[i][j] = 0.5 * (gu[i][axm[j]] + gu[j][axm[i]]);
+              tr += eps[i][i];
+            }
+            double ss = 0.0;
+            if (mode == 1) {
+#pragma unroll
+              for (int i = 0; i < NC; ++i)
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                  const double dv = eps[i][j] - (i == j ? (1.0 / 3.0) * tr : 0.0);
+                  ss = fma(dv, dv, ss);
+                }
+              val = sqrt(2.0 / 3.0 * ss);
+            } else {
+              double trs = 0.0;
+              double sig[NC][NC];
+#pragma unroll
+              for (int i = 0; i < NC; ++i) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j) sig[i][j] = 2.0 * mu * eps[i][j] + (i == j ? lam * tr : 0.0);
+                trs += sig[i][i];
+              }
+#pragma unroll
+              for (int i = 0; i < NC; ++i)
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                  const double dv = sig[i][j] - (i == j ? (1.0 / 3.0) * trs : 0.0);
+                  ss = fma(dv, dv, ss);
+                }
+              val = sqrt(3.0 / 2.0 * ss);
+            }
+          }
+          acc = fma(val, w, acc);
+        }
+      }
+      rhs[idx] = acc;
+    }
+  }
+}
+
+int launch_cell_rhs(pde_ctx* c, const Grid& g, int ncomp, const SimplexGeom& sg, const double* u, double* rhs,
+                    int mode, double lam, double mu, double Emod) {
+  RowLaunch rl = row_launch(c, g);
+  DISPATCH_NC(ncomp, (k_cell_rhs<NC><<<rl.grid, rl.block, 0, c->stream>>>(g, sg, u, rhs, mode, lam, mu, Emod)));
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// mesh / dof-map / boundary-set generation (bit-exact integer + FP64 coordinate expressions)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_mesh_coords(int dim, int n0, int n1, int n2, double L0, double L1, double L2, long long nv, double* __restrict__ out) {
+  const long long nn0 = n0 + 1, nn1 = dim >= 2 ? n1 + 1 : 1;
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (long long)gridDim.x * blockDim.x) {
+    const long long ix = v % nn0, iy = (v / nn0) % nn1, iz = v / (nn0 * nn1);
+    const long long ii[3] = {ix, iy, iz};
+    const double L[3] = {L0, L1, L2};
+    const int n[3] = {n0, n1, n2};
+    for (int k = 0; k < dim; ++k) {
+      double xk;
+      if (dim == 3)  // BoxMesh: a + (i*(b-a))/n   (a = 0)
+        xk = __dadd_rn(0.0, __ddiv_rn(__dmul_rn((double)ii[k], __dsub_rn(L[k], 0.0)), (double)n[k]));
+      else           // IntervalMesh / RectangleMesh: a + ((b-a)/n)*i
+        xk = __dadd_rn(0.0, __dmul_rn(__ddiv_rn(__dsub_rn(L[k], 0.0), (double)n[k]), (double)ii[k]));
+      out[v * dim + k] = xk;
+    }
+  }
+}
+
+int launch_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* out) {
+  int64_t nv, ncell;
+  PDE_OK(pde_mesh_counts(dim, n, &nv, &ncell));
+  int blocks = flat_blocks(c, nv, 256);
+  k_mesh_coords<<<blocks, 256, 0, c->stream>>>(dim, n[0], dim > 1 ? n[1] : 0, dim > 2 ? n[2] : 0, L[0],
+                                                dim > 1 ? L[1] : 0.0, dim > 2 ? L[2] : 0.0, nv, out);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__device__ __forceinline__ void sort_small(long long* v, int n) {
+  for (int i = 1; i < n; ++i) {
+    long long key = v[i];
+    int j = i - 1;
+    while (j >= 0 && v[j] > key) { v[j + 1] = v[j]; --j; }
+    v[j + 1] = key;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_mesh_cells(int dim, int n0, int n1, int n2, long long ngrid, int sorted, int ncomp, int layout, long long nv,
+             int32_t* __restrict__ out) {
+  const int tets[6][4] = {{0, 1, 3, 7}, {0, 1, 7, 5}, {0, 5, 7, 4}, {0, 3, 2, 7}, {0, 6, 4, 7}, {0, 2, 6, 7}};
+  const int tris[2][3] = {{0, 1, 3}, {0, 2, 3}};
+  const int nsimp = dim == 1 ? 1 : (dim == 2 ? 2 : 6);
+  const int nvs = dim + 1;
+  const long long nn0 = n0 + 1, nn1 = n1 + 1;
+  for (long long gcell = (long long)blockIdx.x * blockDim.x + threadIdx.x; gcell < ngrid;
+       gcell += (long long)gridDim.x * blockDim.x) {
+    long long ix = gcell % n0, iy = 0, iz = 0;
+    if (dim >= 2) iy = (gcell / n0) % n1;
+    if (dim == 3) iz = gcell / ((long long)n0 * n1);
+    long long v[8];
+    v[0] = dim == 1 ? ix : (dim == 2 ? iy * nn0 + ix : iz * nn0 * nn1 + iy * nn0 + ix);
+    v[1] = v[0] + 1;
+    v[2] = v[0] + nn0;
+    v[3] = v[1] + nn0;
+    for (int q = 0; q < 4; ++q) v[4 + q] = v[q] + nn0 * nn1;
+    for (int t = 0; t < nsimp; ++t) {
+      long long s[4];
+      for (int a = 0; a < nvs; ++a) s[a] = v[dim == 1 ? a : (dim == 2 ? tris[t][a] : tets[t][a])];
+      if (sorted) sort_small(s, nvs);
+      int32_t* dst = out + (gcell * nsimp + t) * (long long)(nvs * ncomp);
+      for (int cc = 0; cc < ncomp; ++cc)
+        for (int a = 0; a < nvs; ++a)
+          dst[cc * nvs + a] = (int32_t)(ncomp == 1 ? s[a] : (layout == 0 ? cc * nv + s[a] : ncomp * s[a] + cc));
+    }
+  }
+}
+
+int launch_mesh_cells(pde_ctx* c, int dim, const int32_t n[3], int sorted, int ncomp, int layout, int32_t* out) {
+  int64_t nv, ncell;
+  PDE_OK(pde_mesh_counts(dim, n, &nv, &ncell));
+  long long ngrid = ncell / (dim == 1 ? 1 : (dim == 2 ? 2 : 6));
+  int blocks = flat_blocks(c, ngrid, 256);
+  k_mesh_cells<<<blocks, 256, 0, c->stream>>>(dim, n[0], dim > 1 ? n[1] : 1, dim > 2 ? n[2] : 1, ngrid, sorted, ncomp,
+                                               layout, nv, out);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(128)
+k_bc_mask(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, uint8_t* __restrict__ mask,
+          double* __restrict__ vals) {
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      double bcv = 0.0;
+      const bool isdir = bc_node(g, bc, ix, iy, lz + g.z0, &bcv);
+      const long long node = row * g.nn[0] + ix;
+      mask[node] = isdir ? 1 : 0;
+      if (vals) vals[node] = isdir ? bcv : 0.0;
+    }
+  }
+}
+
+int launch_bc_mask(pde_ctx* c, const Grid& g, const BcDev& bc, uint8_t* mask, double* vals) {
+  RowLaunch rl = row_launch(c, g);
+  k_bc_mask<<<rl.grid, rl.block, 0, c->stream>>>(g, bc, mask, vals);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}

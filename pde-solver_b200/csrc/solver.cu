@@ -1,0 +1,383 @@
+// Operators, geometric multigrid hierarchy and the PCG driver.
+//
+// Replaces the linear-algebra half of the reference's `solve(a == L, u, bcs)` calls
+// (fenics_mcp_server.py:265,311,397,440,661,709,1538,1688,1838: assemble AIJ + sparse LU every call)
+// with a matrix-free preconditioned CG whose operator is never stored.
+#include <cmath>
+#include <cstring>
+
+#include "solver.cuh"
+
+int launch_stencil_generic(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
+int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, bool* handled);
+
+int launch_stencil(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
+  if (a.variant == 0) {
+    bool handled = false;
+    PDE_OK(launch_stencil_fast(c, g, bc, op, a, &handled));
+    if (handled) return 0;
+  }
+  return launch_stencil_generic(c, g, bc, op, a);
+}
+
+// ---- Field ---------------------------------------------------------------------------------
+int Field::alloc(const Grid& g, int ncomp) {
+  release();
+  bytes = (size_t)g.comp_stride * ncomp * sizeof(double);
+  CUDA_OK(cudaMalloc(&raw, bytes));
+  CUDA_OK(cudaMemset(raw, 0, bytes));
+  p = raw + g.plane;
+  return 0;
+}
+void Field::release() {
+  if (raw) cudaFree(raw);
+  raw = p = nullptr;
+  bytes = 0;
+}
+
+// ---- Operator --------------------------------------------------------------------------------
+int Operator::upload(pde_ctx* c) {
+  (void)c;
+  const int nc = tab.ncomp, nn = nc * nc;
+  dev.ncomp = nc;
+  dev.gershgorin = tab.gershgorin;
+  std::vector<double> dinv((size_t)PDE_NCLASS * nc, 0.0);
+  for (int cls = 0; cls < PDE_NCLASS; ++cls)
+    for (int i = 0; i < nc; ++i) {
+      double dg = tab.coef[((size_t)cls * PDE_NOFF + 0) * nn + i * nc + i];
+      dinv[cls * nc + i] = dg > 0 ? 1.0 / dg : 0.0;
+    }
+  for (int k = 0; k < PDE_NOFF; ++k)
+    for (int q = 0; q < nn; ++q) dev.h_int[k * nn + q] = tab.coef[((size_t)13 * PDE_NOFF + k) * nn + q];
+  CUDA_OK(cudaMalloc(&dev.coef, tab.coef.size() * sizeof(double)));
+  CUDA_OK(cudaMalloc(&dev.dinv, dinv.size() * sizeof(double)));
+  CUDA_OK(cudaMalloc(&dev.load, PDE_NCLASS * sizeof(double)));
+  CUDA_OK(cudaMemcpy(dev.coef, tab.coef.data(), tab.coef.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dev.dinv, dinv.data(), dinv.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dev.load, tab.load.data(), PDE_NCLASS * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+int Operator::setup_scalar(pde_ctx* c, const Grid& g_, const BcDev& bc_, double alpha, double beta) {
+  release();
+  g = g_;
+  bc = bc_;
+  PDE_OK(build_scalar_table(g.dim, g.h, g.nc, alpha, beta, &tab));
+  return upload(c);
+}
+int Operator::setup_elasticity(pde_ctx* c, const Grid& g_, const BcDev& bc_, double lam, double mu) {
+  release();
+  g = g_;
+  bc = bc_;
+  PDE_OK(build_elasticity_table(g.dim, g.h, g.nc, lam, mu, &tab));
+  return upload(c);
+}
+void Operator::release() {
+  if (dev.coef) cudaFree(dev.coef);
+  if (dev.dinv) cudaFree(dev.dinv);
+  if (dev.load) cudaFree(dev.load);
+  dev.coef = dev.dinv = dev.load = nullptr;
+}
+
+int read_scal(pde_ctx* c, int slot, int count, double* out) {
+  CUDA_OK(cudaMemcpyAsync(c->h_scal + slot, c->scal + slot, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < count; ++i) out[i] = c->h_scal[slot + i];
+  return 0;
+}
+
+// ---- multigrid ---------------------------------------------------------------------------------
+#define PDE_DENSE_MAX 768
+
+static long long count_free_and_index(const Grid& g, const BcDev& bc, int ncomp, std::vector<long long>* idx,
+                                      std::vector<int>* dofid) {
+  long long n = 0;
+  if (dofid) dofid->assign((size_t)g.nn[0] * g.nn[1] * g.nzl * ncomp, -1);
+  for (int lz = 0; lz < g.nzl; ++lz)
+    for (int iy = 0; iy < g.nn[1]; ++iy)
+      for (int ix = 0; ix < g.nn[0]; ++ix) {
+        double v;
+        if (bc_node(g, bc, ix, iy, lz + g.z0, &v)) continue;
+        for (int i = 0; i < ncomp; ++i) {
+          if (idx) idx->push_back((long long)ix + (long long)g.PX * iy + g.plane * lz + i * g.comp_stride);
+          if (dofid) (*dofid)[(((size_t)lz * g.nn[1] + iy) * g.nn[0] + ix) * ncomp + i] = (int)n;
+          ++n;
+        }
+      }
+  return n;
+}
+
+static int dense_inverse_spd(std::vector<double>& A, int n) {
+  // Cholesky A = L L^T (in place, lower), then A^-1 = L^-T L^-1
+  for (int j = 0; j < n; ++j) {
+    double d = A[(size_t)j * n + j];
+    for (int k = 0; k < j; ++k) d -= A[(size_t)j * n + k] * A[(size_t)j * n + k];
+    if (!(d > 0)) return 1;
+    d = std::sqrt(d);
+    A[(size_t)j * n + j] = d;
+    for (int i = j + 1; i < n; ++i) {
+      double s = A[(size_t)i * n + j];
+      for (int k = 0; k < j; ++k) s -= A[(size_t)i * n + k] * A[(size_t)j * n + k];
+      A[(size_t)i * n + j] = s / d;
+    }
+  }
+  std::vector<double> Li((size_t)n * n, 0.0);
+  for (int j = 0; j < n; ++j) {
+    Li[(size_t)j * n + j] = 1.0 / A[(size_t)j * n + j];
+    for (int i = j + 1; i < n; ++i) {
+      double s = 0;
+      for (int k = j; k < i; ++k) s -= A[(size_t)i * n + k] * Li[(size_t)k * n + j];
+      Li[(size_t)i * n + j] = s / A[(size_t)i * n + i];
+    }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = 0;
+      for (int k = i; k < n; ++k) s += Li[(size_t)k * n + i] * Li[(size_t)k * n + j];
+      A[(size_t)i * n + j] = A[(size_t)j * n + i] = s;
+    }
+  return 0;
+}
+
+static int build_dense_coarse(MGLevel& L) {
+  const Grid& g = L.op.g;
+  const int nc = L.op.tab.ncomp, nn = nc * nc;
+  std::vector<long long> idx;
+  std::vector<int> dofid;
+  long long n = count_free_and_index(g, L.op.bc, nc, &idx, &dofid);
+  std::vector<double> A((size_t)n * n, 0.0);
+  for (int lz = 0; lz < g.nzl; ++lz)
+    for (int iy = 0; iy < g.nn[1]; ++iy)
+      for (int ix = 0; ix < g.nn[0]; ++ix) {
+        const size_t node = ((size_t)lz * g.nn[1] + iy) * g.nn[0] + ix;
+        if (dofid[node * nc] < 0) continue;
+        const int cls = node_class(g, ix, iy, lz + g.z0);
+        for (int k = 0; k < g.nk; ++k) {
+          int jx = ix + g.kdx[k], jy = iy + g.kdy[k], jz = lz + g.kdz[k];
+          if (jx < 0 || jx >= g.nn[0] || jy < 0 || jy >= g.nn[1] || jz < 0 || jz >= g.nzl) continue;
+          const size_t nb = ((size_t)jz * g.nn[1] + jy) * g.nn[0] + jx;
+          if (dofid[nb * nc] < 0) continue;
+          const double* cf = &L.op.tab.coef[((size_t)cls * PDE_NOFF + g.kidx[k]) * nn];
+          for (int i = 0; i < nc; ++i)
+            for (int j = 0; j < nc; ++j) A[(size_t)dofid[node * nc + i] * n + dofid[nb * nc + j]] += cf[i * nc + j];
+        }
+      }
+  if (dense_inverse_spd(A, (int)n)) PDE_FAIL("coarse operator is not positive definite");
+  L.n_dense = (int)n;
+  CUDA_OK(cudaMalloc(&L.Ainv, A.size() * sizeof(double)));
+  CUDA_OK(cudaMalloc(&L.idx, idx.size() * sizeof(long long)));
+  CUDA_OK(cudaMemcpy(L.Ainv, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(L.idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, double p1) {
+  release();
+  const int dim = fine.g.dim;
+  int ax[3], nax;
+  internal_axes(dim, ax, &nax);
+  int32_t n[3] = {0, 0, 0};
+  double Lu[3] = {1, 1, 1};
+  for (int q = 0; q < nax; ++q) {
+    n[q] = fine.g.nc[ax[q]];
+    Lu[q] = fine.g.h[ax[q]] * fine.g.nc[ax[q]];
+  }
+  const int ncomp = fine.tab.ncomp;
+  for (int level = 0;; ++level) {
+    std::unique_ptr<MGLevel> L(new MGLevel());
+    Grid g;
+    PDE_OK(make_grid(dim, n, Lu, c->rank, c->world, &g));
+    if (kind == PDE_OP_ELASTICITY) PDE_OK(L->op.setup_elasticity(c, g, fine.bc, p0, p1));
+    else PDE_OK(L->op.setup_scalar(c, g, fine.bc, p0, p1));
+    PDE_OK(L->xa.alloc(g, ncomp));
+    PDE_OK(L->xb.alloc(g, ncomp));
+    PDE_OK(L->d.alloc(g, ncomp));
+    PDE_OK(L->r.alloc(g, ncomp));
+    if (level > 0) PDE_OK(L->b.alloc(g, ncomp));
+    lv.push_back(std::move(L));
+    // can we coarsen further?
+    bool can = c->world == 1;
+    int32_t nc2[3] = {0, 0, 0};
+    for (int q = 0; q < nax; ++q) {
+      if (n[q] % 2 != 0 || n[q] < 2) can = false;
+      nc2[q] = n[q] / 2;
+    }
+    if (can) {
+      Grid gc;
+      PDE_OK(make_grid(dim, nc2, Lu, c->rank, c->world, &gc));
+      long long nodes = (long long)gc.nn[0] * gc.nn[1] * gc.nzl;
+      if (nodes <= 200000) {
+        long long nfree = count_free_and_index(gc, fine.bc, ncomp, nullptr, nullptr);
+        if (nfree <= 0) can = false;
+      }
+    }
+    if (!can) break;
+    for (int q = 0; q < nax; ++q) n[q] = nc2[q];
+  }
+  // coarsest level: dense inverse if small enough
+  MGLevel& Lc = *lv.back();
+  long long nodes = (long long)Lc.op.g.nn[0] * Lc.op.g.nn[1] * Lc.op.g.nzl;
+  if (lv.size() > 1 && nodes * ncomp <= 4 * PDE_DENSE_MAX) {
+    long long nfree = count_free_and_index(Lc.op.g, Lc.op.bc, ncomp, nullptr, nullptr);
+    if (nfree > 0 && nfree <= PDE_DENSE_MAX) PDE_OK(build_dense_coarse(Lc));
+  }
+  return 0;
+}
+
+void Hierarchy::release() {
+  for (auto& L : lv) {
+    L->op.release();
+    L->b.release(); L->xa.release(); L->xb.release(); L->r.release(); L->d.release();
+    if (L->Ainv) cudaFree(L->Ainv);
+    if (L->idx) cudaFree(L->idx);
+  }
+  lv.clear();
+}
+
+struct Cheby {
+  double theta, delta, sigma, rho;
+  void init(double lmax, double ratio) {
+    const double lmin = lmax / ratio;
+    theta = 0.5 * (lmax + lmin);
+    delta = 0.5 * (lmax - lmin);
+    sigma = theta / delta;
+    rho = 1.0 / sigma;
+  }
+  // coefficients of sweep k (k = 0 restarts the recurrence): d = c1 d + c2 Dinv r
+  void coef(int k, double* c1, double* c2) {
+    if (k == 0) { rho = 1.0 / sigma; *c1 = 0.0; *c2 = 1.0 / theta; return; }
+    const double rn = 1.0 / (2.0 * sigma - rho);
+    *c1 = rn * rho;
+    *c2 = 2.0 * rn / delta;
+    rho = rn;
+  }
+};
+
+static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double** oth, int sweeps, bool zero_guess,
+                  double ratio) {
+  Cheby ch;
+  ch.init(L.op.dev.gershgorin, ratio);
+  int k0 = 0;
+  if (zero_guess) {
+    double c1, c2;
+    ch.coef(0, &c1, &c2);
+    PDE_OK(launch_cheby_first(c, L.op.g, L.op.bc, L.op.dev, b, L.d.p, *cur, c2));
+    k0 = 1;
+  }
+  for (int k = k0; k < sweeps; ++k) {
+    StencilArgs a;
+    a.cheby = 1;
+    a.x = *cur; a.y = *oth; a.b = b; a.d = L.d.p;
+    ch.coef(k, &a.c1, &a.c2);
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, *cur));
+    PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
+    std::swap(*cur, *oth);
+  }
+  return 0;
+}
+
+int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double** z_out) {
+  (void)fine;
+  const int nl = (int)lv.size();
+  std::vector<double*> cur(nl), oth(nl);
+  for (int l = 0; l < nl; ++l) { cur[l] = lv[l]->xa.p; oth[l] = lv[l]->xb.p; }
+  for (int l = 0; l < nl - 1; ++l) {
+    MGLevel& L = *lv[l];
+    const double* b = l == 0 ? b0 : L.b.p;
+    PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, true, ratio));
+    StencilArgs a;
+    a.x = cur[l]; a.b = b; a.y = L.r.p; a.bscale = 1.0; a.ascale = -1.0;
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, cur[l]));
+    PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, L.r.p));
+    PDE_OK(launch_restrict(c, L.op.g, lv[l + 1]->op.g, lv[l + 1]->op.bc, L.op.dev.ncomp, L.r.p, lv[l + 1]->b.p));
+  }
+  {
+    MGLevel& L = *lv[nl - 1];
+    const double* b = nl == 1 ? b0 : L.b.p;
+    if (L.n_dense > 0) PDE_OK(launch_dense_solve(c, L.n_dense, L.Ainv, L.idx, b, cur[nl - 1]));
+    else PDE_OK(smooth(c, L, b, &cur[nl - 1], &oth[nl - 1], nl == 1 ? nu : coarse_sweeps, true, nl == 1 ? ratio : 30.0));
+  }
+  for (int l = nl - 2; l >= 0; --l) {
+    MGLevel& L = *lv[l];
+    const double* b = l == 0 ? b0 : L.b.p;
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, lv[l + 1]->op.g, L.op.dev.ncomp, cur[l + 1]));
+    PDE_OK(launch_prolong_add(c, L.op.g, lv[l + 1]->op.g, L.op.bc, L.op.dev.ncomp, cur[l + 1], cur[l]));
+    PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, false, ratio));
+  }
+  *z_out = cur[0];
+  return 0;
+}
+
+int choose_precond(const pde_solver_opts& o, pde_ctx* c, long long ndofs, const Hierarchy& h) {
+  if (o.precond == PDE_PRECOND_JACOBI) return PDE_PRECOND_JACOBI;
+  if (h.levels() < 2) return PDE_PRECOND_JACOBI;
+  if (o.precond == PDE_PRECOND_GMG) return PDE_PRECOND_GMG;
+  (void)c;
+  return ndofs >= 20000 ? PDE_PRECOND_GMG : PDE_PRECOND_JACOBI;
+}
+
+// ---- PCG -----------------------------------------------------------------------------------------
+int PcgWork::alloc(const Grid& g, int ncomp) {
+  PDE_OK(p.alloc(g, ncomp));
+  PDE_OK(q.alloc(g, ncomp));
+  return 0;
+}
+void PcgWork::release() { p.release(); q.release(); }
+
+int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* x, double* r, double bnorm2,
+              const pde_solver_opts& o, pde_stats* st) {
+  const Grid& g = A.g;
+  const int nc = A.dev.ncomp;
+  const bool gmg = mg != nullptr;
+  const double tol2 = o.rtol * o.rtol * bnorm2;
+  st->solves += 1;
+  st->levels = gmg ? mg->levels() : 1;
+  if (!(bnorm2 > 0.0)) {  // zero right-hand side: the initial guess (Dirichlet lift) is the solution
+    st->final_relres = 0.0;
+    return 0;
+  }
+  double* z = nullptr;
+  double rr;
+  if (!gmg) {
+    CUDA_OK(cudaMemsetAsync(c->scal + S_XY, 0, 2 * sizeof(double), c->stream));
+    PDE_OK(launch_cg_update(c, g, A.dev, x, r, w.p.p, w.q.p, S_RHO0, S_XY, S_RHO0, S_RHO0 + 1, 1));
+    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_RHO0, 2));
+    PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, r, S_RHO0, S_RHO0, 1, 1));
+  } else {
+    PDE_OK(mg->vcycle(c, A, r, &z));
+    PDE_OK(launch_dot(c, g, nc, r, z, S_RHO0));
+    PDE_OK(launch_dot(c, g, nc, r, r, S_RHO0 + 1));
+    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_RHO0, 2));
+    PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, z, S_RHO0, S_RHO0, 1, 0));
+  }
+  PDE_OK(read_scal(c, S_RHO0 + 1, 1, &rr));
+  int it = 0;
+  bool conv = rr <= tol2;
+  const int check = gmg ? 1 : (o.check_every > 0 ? o.check_every : 10);
+  while (!conv && it < o.max_iters) {
+    const int sr = 2 * (it & 1), sn = 2 * (1 - (it & 1));
+    StencilArgs a;
+    a.x = w.p.p; a.y = w.q.p; a.reduce_slot_xy = S_XY;
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, w.p.p));
+    PDE_OK(launch_stencil(c, g, A.bc, A.dev, a));
+    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 1));
+    PDE_OK(launch_cg_update(c, g, A.dev, x, r, w.p.p, w.q.p, sr, S_XY, sn, sn + 1, !gmg));
+    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 2));
+    if (gmg) {
+      PDE_OK(mg->vcycle(c, A, r, &z));
+      PDE_OK(launch_dot(c, g, nc, r, z, sn));
+      if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 1));
+    }
+    PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, gmg ? z : r, sr, sn, 0, !gmg));
+    ++it;
+    if (it % check == 0 || it >= o.max_iters) {
+      PDE_OK(read_scal(c, sn + 1, 1, &rr));
+      if (!(rr == rr)) PDE_FAIL("PCG broke down (NaN residual)");
+      conv = rr <= tol2;
+    }
+  }
+  st->iters_total += it;
+  st->final_relres = std::sqrt(rr / bnorm2);
+  if (!conv) st->converged = 0;
+  return 0;
+}

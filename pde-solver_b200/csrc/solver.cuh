@@ -1,0 +1,60 @@
+// Solver-layer objects: device fields, operators, multigrid hierarchy, PCG.
+#pragma once
+#include <memory>
+
+#include "device.cuh"
+
+struct Field {
+  double* raw = nullptr;  // allocation start (ghost plane of component 0)
+  double* p = nullptr;    // plane 0 of component 0
+  size_t bytes = 0;
+  int alloc(const Grid& g, int ncomp);
+  void release();
+};
+
+struct Operator {
+  Grid g{};
+  BcDev bc{};
+  OpDev dev{};
+  OpTable tab;
+  int setup_scalar(pde_ctx* c, const Grid& g, const BcDev& bc, double alpha, double beta);
+  int setup_elasticity(pde_ctx* c, const Grid& g, const BcDev& bc, double lam, double mu);
+  int upload(pde_ctx* c);
+  void release();
+};
+
+struct MGLevel {
+  Operator op;
+  Field b, xa, xb, r, d;
+  // coarsest level
+  int n_dense = 0;
+  double* Ainv = nullptr;
+  long long* idx = nullptr;
+};
+
+struct Hierarchy {
+  std::vector<std::unique_ptr<MGLevel>> lv;
+  int nu = 2;
+  double ratio = 8.0;
+  int coarse_sweeps = 8;
+  // build levels 1.. from a fine operator description; level 0 uses the caller's operator
+  int build(pde_ctx* c, const Operator& fine, int kind, double p0, double p1);
+  // z = V(b0) ; returns pointer to the buffer holding z (one of level-0 xa/xb)
+  int vcycle(pde_ctx* c, const Operator& fine, const double* b0, double** z_out);
+  int levels() const { return (int)lv.size(); }
+  void release();
+};
+
+struct PcgWork {
+  Field p, q;
+  int alloc(const Grid& g, int ncomp);
+  void release();
+};
+
+// Solves A x = b given x (initial guess incl. Dirichlet values) and r = masked(b - A x).
+// bnorm2 = ||b||^2 for the stopping rule ||r|| <= rtol ||b||.
+int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* x, double* r, double bnorm2,
+              const pde_solver_opts& o, pde_stats* st);
+
+int read_scal(pde_ctx* c, int slot, int count, double* out);
+int choose_precond(const pde_solver_opts& o, pde_ctx* c, long long ndofs, const Hierarchy& h);

@@ -1,0 +1,72 @@
+"""Structured simplicial meshes, P1 dof maps and Dirichlet sets, generated on the GPU.
+
+Mirrors what the reference obtains from DOLFIN (fenics_mcp_server.py:229-230, 369-370, 533-535,
+1649-1650, 1804-1805, 233-241, 373-376, 606-628): IntervalMesh / RectangleMesh("right") / BoxMesh
+vertex coordinates and connectivity, FunctionSpace / VectorFunctionSpace cell-dof tables, and the
+topological DirichletBC vertex sets.  Numbering is DOLFIN's with reorder_dofs_serial=False."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _n3(n):
+    return list(n) + [0] * (3 - len(n))
+
+
+def coordinates(dim, n, L, ctx=None):
+    """(nverts, dim) float64, bit-exact DOLFIN expressions."""
+    ctx = ctx or _lib.default_context()
+    nv, _ = _lib.mesh_counts(dim, n)
+    out = np.empty((nv, dim), dtype=np.float64)
+    _lib.check(_lib.lib().pde_mesh_coords(ctx.handle, int(dim), _lib.i3(n), _lib.d3(L), _lib.ptr(out)))
+    return out
+
+
+def cells(dim, n, ordered=True, ctx=None):
+    """(ncells, dim+1) int32 connectivity; ordered=True is the state after mesh.order()."""
+    ctx = ctx or _lib.default_context()
+    _, nc = _lib.mesh_counts(dim, n)
+    out = np.empty((nc, dim + 1), dtype=np.int32)
+    _lib.check(_lib.lib().pde_mesh_cells(ctx.handle, int(dim), _lib.i3(n), 1 if ordered else 0, _lib.ptr(out)))
+    return out
+
+
+def cell_dofs(dim, n, ncomp=1, layout="blocked", ctx=None):
+    """(ncells, ncomp*(dim+1)) int32 P1 cell-dof table; layout 'blocked' (UFC) or 'interleaved'."""
+    ctx = ctx or _lib.default_context()
+    _, nc = _lib.mesh_counts(dim, n)
+    out = np.empty((nc, ncomp * (dim + 1)), dtype=np.int32)
+    _lib.check(_lib.lib().pde_dofmap_cells(ctx.handle, int(dim), _lib.i3(n), int(ncomp),
+                                            0 if layout == "blocked" else 1, _lib.ptr(out)))
+    return out
+
+
+def dirichlet(dim, n, bc, ctx=None):
+    """(mask uint8 [nverts], values float64 [nverts]) of a pde_bc specification."""
+    ctx = ctx or _lib.default_context()
+    nv, _ = _lib.mesh_counts(dim, n)
+    mask = np.empty(nv, dtype=np.uint8)
+    vals = np.empty(nv, dtype=np.float64)
+    _lib.check(_lib.lib().pde_boundary_mask(ctx.handle, int(dim), _lib.i3(n), C.byref(bc), _lib.ptr(mask),
+                                             _lib.ptr(vals)))
+    return mask, vals
+
+
+def heat_bc(dim, T_boundary=0.0, T_left=None, T_right=None, T_side=None):
+    """The reference's heat DirichletBC lists as a pde_bc (1D: left/right :233-241; 2D: all :373-376;
+    3D: all, or directional left/right/other_faces :576-628)."""
+    if dim == 1:
+        return _lib.make_bc({0: T_left, 1: T_right})
+    if dim == 3 and (T_left is not None or T_right is not None or T_side is not None):
+        faces = {}
+        if T_left is not None:
+            faces[0] = T_left
+        if T_right is not None:
+            faces[1] = T_right
+        if T_side is not None:
+            for f in (2, 3, 4, 5):
+                faces[f] = T_side
+        return _lib.make_bc(faces, side_excludes_xends=True)
+    return _lib.make_bc({f: T_boundary for f in range(2 * dim)})

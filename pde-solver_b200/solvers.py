@@ -1,0 +1,217 @@
+"""Host-side mirror of the reference's raw solvers (same names, arguments and result type).
+
+Reference: /root/reference/fenics_mcp_server.py
+  _solve_heat_1d_raw :204-338      _solve_heat_2d_raw :345-468      _solve_heat_3d_raw :475-762
+  _solve_elasticity_1d_static :1470-1587   _2d_ :1593-1743   _3d_ :1749-1892
+Each function only marshals arguments into the C ABI (include/pde_b200.h) and wraps the result;
+all arithmetic runs in hand-written CUDA.  Extra keyword-only arguments (rtol, precond,
+snapshot_stride, as_arrays) are additions the reference does not have; their defaults reproduce
+the reference's behaviour."""
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import _lib, mesh
+from .fields import TimeSeriesField
+
+# above this many stored values the result keeps NumPy arrays instead of nested Python lists
+LIST_LIMIT = int(os.environ.get("PDE_B200_LIST_LIMIT", "4000000"))
+
+_last_stats = {}
+
+
+def last_stats():
+    """Solver statistics (iterations, residuals, device time, launches) of the most recent call."""
+    return dict(_last_stats)
+
+
+def _embed3(coords, dim):
+    out = np.zeros((coords.shape[0], 3), dtype=np.float64)
+    out[:, :dim] = coords
+    return out
+
+
+def _finish(coords3, values, times, dim, meta, as_arrays):
+    if as_arrays is None:
+        as_arrays = values.size > LIST_LIMIT
+    if as_arrays:
+        return TimeSeriesField(coords=coords3, values=values, times=np.asarray(times), dim=dim, meta=meta)
+    return TimeSeriesField(coords=coords3.tolist(), values=values.tolist(), times=[float(t) for t in times],
+                           dim=dim, meta=meta)
+
+
+def _heat(dim, L, n, diffusivity, T_initial, dt, num_steps, steady, source_type, source_value, initial_type,
+          initial_amplitude, initial_wavenumber, bc, rtol, precond, snapshot_stride, u0=None, ctx=None):
+    ctx = ctx or _lib.default_context()
+    p = _lib.HeatParams()
+    p.dim = dim
+    p.n = _lib.i3(n)
+    p.L = _lib.d3(L)
+    p.diffusivity = float(diffusivity)
+    p.dt = float(dt)
+    p.num_steps = int(num_steps)
+    p.steady = 1 if steady else 0
+    p.source_value = float(source_value) if source_type == "constant" else 0.0
+    if u0 is not None:
+        p.initial_type = _lib.IC["array"]
+    else:
+        p.initial_type = _lib.IC.get(initial_type, _lib.IC["constant"])
+    p.snapshot_stride = int(snapshot_stride)
+    p.T_initial = float(T_initial)
+    p.initial_amplitude = float(initial_amplitude)
+    p.initial_wavenumber = float(initial_wavenumber)
+    p.bc = bc
+    nv, _ = _lib.mesh_counts(dim, n)
+    nsnap = 1 if steady else 1 + int(num_steps) // max(1, int(snapshot_stride))
+    values = np.empty((nsnap, nv), dtype=np.float64)
+    times = np.empty(nsnap, dtype=np.float64)
+    st = _lib.Stats()
+    o = _lib.make_opts(rtol=rtol, precond=precond)
+    u0a = np.ascontiguousarray(u0, dtype=np.float64) if u0 is not None else None
+    _lib.check(_lib.lib().pde_heat_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(u0a), _lib.ptr(values),
+                                         _lib.ptr(times), C.byref(st)))
+    _last_stats.clear()
+    _last_stats.update(st.as_dict())
+    coords = mesh.coordinates(dim, n, L, ctx)
+    return coords, values, times
+
+
+def _solve_heat_1d_raw(length: float, nx: int, diffusivity: float, T_left: float, T_right: float,
+                       T_initial: float, dt: float, num_steps: int, steady: bool = False,
+                       source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
+                       initial_amplitude: float = 1.0, initial_wavenumber: float = 1.0, *, rtol: float = 1e-10,
+                       precond: str = "auto", snapshot_stride: int = 1, as_arrays: Optional[bool] = None,
+                       u0=None) -> TimeSeriesField:
+    """1D heat equation on [0, length], Dirichlet T_left / T_right, backward Euler or steady."""
+    bc = mesh.heat_bc(1, T_left=T_left, T_right=T_right)
+    coords, values, times = _heat(1, [length], [nx], diffusivity, T_initial, dt, num_steps, steady, source_type,
+                                  source_value, initial_type, initial_amplitude, initial_wavenumber, bc, rtol,
+                                  precond, snapshot_stride, u0)
+    # the reference sorts dofs by x (:252-254); natural order is already sorted
+    order = np.argsort(coords[:, 0], kind="stable")
+    meta = {"name": "temperature", "unit": "°C", "pde": "heat", "coordinate_system": "cartesian",
+            "length": length, "source_type": source_type, "source_value": source_value, "steady": steady}
+    return _finish(_embed3(coords[order], 1), values[:, order], times, 1, meta, as_arrays)
+
+
+def _solve_heat_2d_raw(Lx: float, Ly: float, nx: int, ny: int, diffusivity: float, T_boundary: float,
+                       T_initial: float, dt: float, num_steps: int, steady: bool = False,
+                       source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
+                       initial_amplitude: float = 1.0, initial_wavenumber: float = 1.0, *, rtol: float = 1e-10,
+                       precond: str = "auto", snapshot_stride: int = 1, as_arrays: Optional[bool] = None,
+                       u0=None) -> TimeSeriesField:
+    """2D heat equation on [0,Lx]x[0,Ly], constant Dirichlet value on the whole boundary."""
+    bc = mesh.heat_bc(2, T_boundary=T_boundary)
+    coords, values, times = _heat(2, [Lx, Ly], [nx, ny], diffusivity, T_initial, dt, num_steps, steady,
+                                  source_type, source_value, initial_type, initial_amplitude, initial_wavenumber,
+                                  bc, rtol, precond, snapshot_stride, u0)
+    meta = {"name": "temperature", "unit": "°C", "pde": "heat", "coordinate_system": "cartesian", "Lx": Lx,
+            "Ly": Ly, "source_type": source_type, "source_value": source_value, "steady": steady}
+    return _finish(_embed3(coords, 2), values, times, 2, meta, as_arrays)
+
+
+def _solve_heat_3d_raw(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: int, diffusivity: float,
+                       T_boundary: float, T_initial: float, dt: float, num_steps: int, steady: bool = False,
+                       source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
+                       initial_amplitude: float = 1.0, initial_wavenumber: float = 1.0,
+                       geometry_type: str = "box", cylinder_radius: Optional[float] = None,
+                       T_left: Optional[float] = None, T_right: Optional[float] = None,
+                       T_side: Optional[float] = None, core_radius: Optional[float] = None,
+                       core_diffusivity: Optional[float] = None, *, rtol: float = 1e-10, precond: str = "auto",
+                       snapshot_stride: int = 1, as_arrays: Optional[bool] = None, u0=None) -> TimeSeriesField:
+    """3D heat equation on the box [0,Lx]x[0,Ly]x[0,Lz]; uniform or directional Dirichlet values."""
+    if geometry_type == "cylinder" and cylinder_radius is not None:
+        raise NotImplementedError(
+            "geometry_type='cylinder' (mshr / radially weighted forms, reference :512-530, 642-645) is outside "
+            "the structured-box hot path of this build")
+    if core_radius is not None and core_diffusivity is not None:
+        raise NotImplementedError(
+            "composite core (DG0 variable diffusivity, reference :537-572) is outside the uniform-kappa hot path")
+    bc = mesh.heat_bc(3, T_boundary=T_boundary, T_left=T_left, T_right=T_right, T_side=T_side)
+    coords, values, times = _heat(3, [Lx, Ly, Lz], [nx, ny, nz], diffusivity, T_initial, dt, num_steps, steady,
+                                  source_type, source_value, initial_type, initial_amplitude, initial_wavenumber,
+                                  bc, rtol, precond, snapshot_stride, u0)
+    use_directional_bc = (T_left is not None or T_right is not None or T_side is not None)
+    meta = {"name": "temperature", "unit": "°C", "pde": "heat",
+            "coordinate_system": "cartesian" if geometry_type == "box" else "cylindrical",
+            "Lx": Lx, "Ly": Ly, "Lz": Lz, "geometry_type": geometry_type, "source_type": source_type,
+            "source_value": source_value, "steady": steady}
+    if use_directional_bc:
+        for k, v in (("T_left", T_left), ("T_right", T_right), ("T_side", T_side)):
+            if v is not None:
+                meta[k] = v
+    else:
+        meta["T_boundary"] = T_boundary
+    meta["diffusivity"] = diffusivity
+    return _finish(coords, values, times, 3, meta, as_arrays)
+
+
+def _elasticity(dim, L, n, E, nu, body, quantity, plane_stress=True, area=1.0, rtol=1e-10, precond="auto",
+                want_displacement=False, ctx=None):
+    ctx = ctx or _lib.default_context()
+    p = _lib.ElastParams()
+    p.dim = dim
+    p.n = _lib.i3(n)
+    p.L = _lib.d3(L)
+    p.E = float(E)
+    p.nu = float(nu)
+    p.body = _lib.d3(body, 0.0)
+    p.quantity = 1 if quantity == "strain" else 0
+    p.plane_stress = 1 if plane_stress else 0
+    p.area = float(area)
+    nv, _ = _lib.mesh_counts(dim, n)
+    out = np.empty(nv, dtype=np.float64)
+    disp = np.empty((nv, dim), dtype=np.float64) if want_displacement else None
+    st, sp = _lib.Stats(), _lib.Stats()
+    o = _lib.make_opts(rtol=rtol, precond=precond)
+    _lib.check(_lib.lib().pde_elasticity_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(out), _lib.ptr(disp),
+                                               C.byref(st), C.byref(sp)))
+    _last_stats.clear()
+    _last_stats.update(st.as_dict())
+    _last_stats["projection"] = sp.as_dict()
+    coords = mesh.coordinates(dim, n, L, ctx)
+    return coords, out, disp
+
+
+def _solve_elasticity_1d_static(L: float, nx: int, E: float, area: float, body_force: float,
+                                quantity: str = "stress", *, rtol: float = 1e-10, precond: str = "auto",
+                                as_arrays: Optional[bool] = None) -> TimeSeriesField:
+    """Axial bar -(EA u')' = body_force, u(0) = 0; output the projected axial stress or strain."""
+    coords, val, _ = _elasticity(1, [L], [nx], E, 0.0, [body_force], quantity, area=area, rtol=rtol,
+                                 precond=precond)
+    order = np.argsort(coords[:, 0], kind="stable")
+    if quantity == "strain":
+        name, unit = "axial_strain", "-"
+    else:
+        name, unit = "axial_stress", "Pa"
+    meta = {"name": name, "unit": unit, "pde": "elasticity_1d", "L": L, "E": E, "area": area,
+            "body_force": body_force, "quantity": quantity}
+    return _finish(_embed3(coords[order], 1), val[order][None, :], [0.0], 1, meta, as_arrays)
+
+
+def _solve_elasticity_2d_static(Lx: float, Ly: float, nx: int, ny: int, E: float, nu: float, body_fx: float = 0.0,
+                                body_fy: float = 0.0, quantity: str = "stress", plane_stress: bool = True, *,
+                                rtol: float = 1e-10, precond: str = "auto",
+                                as_arrays: Optional[bool] = None) -> TimeSeriesField:
+    """Plane stress/strain static elasticity clamped at x = 0; projected von Mises stress or strain."""
+    coords, val, _ = _elasticity(2, [Lx, Ly], [nx, ny], E, nu, [body_fx, body_fy], quantity,
+                                 plane_stress=plane_stress, rtol=rtol, precond=precond)
+    name, unit = ("von_mises_strain", "-") if quantity == "strain" else ("von_mises_stress", "Pa")
+    meta = {"name": name, "unit": unit, "pde": "elasticity_2d", "Lx": Lx, "Ly": Ly, "E": E, "nu": nu,
+            "body_fx": body_fx, "body_fy": body_fy, "quantity": quantity, "plane_stress": plane_stress}
+    return _finish(_embed3(coords, 2), val[None, :], [0.0], 2, meta, as_arrays)
+
+
+def _solve_elasticity_3d_static(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: int, E: float, nu: float,
+                                body_fx: float = 0.0, body_fy: float = 0.0, body_fz: float = 0.0,
+                                quantity: str = "stress", *, rtol: float = 1e-10, precond: str = "auto",
+                                as_arrays: Optional[bool] = None) -> TimeSeriesField:
+    """3D static elasticity on a box clamped at x = 0; projected von Mises stress or strain."""
+    coords, val, _ = _elasticity(3, [Lx, Ly, Lz], [nx, ny, nz], E, nu, [body_fx, body_fy, body_fz], quantity,
+                                 rtol=rtol, precond=precond)
+    name, unit = ("von_mises_strain", "-") if quantity == "strain" else ("von_mises_stress", "Pa")
+    meta = {"name": name, "unit": unit, "pde": "elasticity_3d", "Lx": Lx, "Ly": Ly, "Lz": Lz, "E": E, "nu": nu,
+            "body_fx": body_fx, "body_fy": body_fy, "body_fz": body_fz, "quantity": quantity}
+    return _finish(coords, val[None, :], [0.0], 3, meta, as_arrays)

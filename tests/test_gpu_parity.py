@@ -1,0 +1,221 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): mesh / dof maps / boundary sets bit-exact; nodal solutions within
+1e-8 relative L2 of the direct-LU oracle at solver rtol 1e-10."""
+import numpy as np
+import pytest
+
+from oracle import fem_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-8  # relative L2, FP64, north_star
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pde_solver_b200 as p
+    return p
+
+
+@pytest.fixture(scope="module")
+def ctx(P):
+    return P._lib.default_context()
+
+
+# ---------------------------------------------------------------- meshes / dof maps / boundary sets
+@pytest.mark.parametrize("dim,n,L", [(1, [100], [2.0]), (1, [7], [0.3]), (2, [5, 3], [1.0, 0.6]),
+                                     (2, [10, 10], [0.2, 0.2]), (3, [4, 3, 2], [1.0, 0.2, 0.2]),
+                                     (3, [10, 7, 5], [0.3, 0.2, 0.7]), (3, [1, 1, 1], [1, 1, 1])])
+def test_mesh_bit_exact(P, dim, n, L):
+    m = fo.make_mesh(dim, L, n)
+    assert np.array_equal(P.mesh.coordinates(dim, n, L), m.coords)          # FP64 bit-exact
+    assert np.array_equal(P.mesh.cells(dim, n, ordered=False), m.cells_raw)
+    assert np.array_equal(P.mesh.cells(dim, n, ordered=True), m.cells)
+    assert np.array_equal(P.mesh.cell_dofs(dim, n, 1), fo.cell_dofs_scalar(m))
+    if dim > 1:
+        for layout in ("blocked", "interleaved"):
+            assert np.array_equal(P.mesh.cell_dofs(dim, n, dim, layout), fo.cell_dofs_vector(m, dim, layout))
+
+
+@pytest.mark.parametrize("dim,n", [(1, [9]), (2, [5, 4]), (3, [4, 3, 2]), (3, [2, 3, 2]), (3, [3, 1, 1])])
+def test_boundary_sets_bit_exact(P, dim, n):
+    L = [1.0, 0.7, 0.4][:dim]
+    m = fo.make_mesh(dim, L, n)
+    cases = [dict(T_boundary=3.0)] if dim > 1 else [dict(T_left=20.0, T_right=1.0)]
+    if dim == 3:
+        cases += [dict(T_left=1.0), dict(T_side=2.0), dict(T_left=1.0, T_right=2.0, T_side=3.0),
+                  dict(T_right=4.0, T_side=5.0)]
+    for kw in cases:
+        dofs, vals = fo._merge_bcs(fo.heat_bcs(m, L, **kw), m.nv)
+        mask, v = P.mesh.dirichlet(dim, n, P.mesh.heat_bc(dim, **kw))
+        assert np.array_equal(np.nonzero(mask)[0], dofs), kw
+        assert np.array_equal(v[dofs], vals), kw
+    # elasticity clamp: near(x[0], 0) plane
+    clamp = fo.dirichlet_dofs(m, lambda x, ob: fo.near(x[:, 0], 0.0))
+    mask, _ = P.mesh.dirichlet(dim, n, P._lib.make_bc({0: 0.0}))
+    assert np.array_equal(np.nonzero(mask)[0], clamp)
+
+
+# ---------------------------------------------------------------- operator application
+def _oracle_matrix(kind, dim, n, L, alpha, beta, lam, mu):
+    m = fo.make_mesh(dim, L, n)
+    if kind == "elasticity":
+        A = fo.assemble_elasticity(m, lam, mu)      # interleaved dofs
+        nv = m.nv
+        perm = (np.arange(dim)[:, None] + dim * np.arange(nv)[None, :]).ravel()   # blocked -> interleaved
+        return m, A[perm][:, perm].tocsr()
+    K, M = fo.assemble_stiffness_mass(m)
+    return m, (alpha * M + beta * K).tocsr()
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("kind,dim,n", [("heat", 1, [33]), ("heat", 2, [17, 9]), ("heat", 3, [9, 6, 7]),
+                                        ("heat", 3, [40, 12, 10]), ("mass", 3, [5, 5, 5]),
+                                        ("stiffness", 2, [8, 8]), ("elasticity", 2, [9, 7]),
+                                        ("elasticity", 3, [6, 5, 4]), ("elasticity", 3, [36, 6, 5]),
+                                        ("heat", 3, [1, 1, 1]), ("elasticity", 3, [2, 1, 3])])
+def test_operator_apply_matches_oracle(P, ctx, kind, dim, n, variant):
+    L = [1.0, 0.6, 0.35][:dim]
+    alpha, beta = (1.0, 0.013) if kind == "heat" else ((1.0, 0.0) if kind == "mass" else (0.0, 1.0))
+    lam, mu = fo.lame(210e9, 0.3, 3)
+    m, A = _oracle_matrix(kind, dim, n, L, alpha, beta, lam, mu)
+    nc = dim if kind == "elasticity" else 1
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((nc, m.nv))
+    for bc, dofs in ((None, np.array([], dtype=int)),
+                     (P._lib.make_bc({0: 0.0}), fo.dirichlet_dofs(m, lambda xx, ob: fo.near(xx[:, 0], 0.0))),
+                     (P._lib.make_bc({f: 0.0 for f in range(2 * dim)}),
+                      fo.dirichlet_dofs(m, lambda xx, ob: np.ones(xx.shape[0], bool)))):
+        p = P._lib.op_params(kind, dim, n, L, alpha, beta, lam, mu, bc=bc, variant=variant)
+        y = P._lib.op_apply(ctx, p, x)
+        ref = (A @ x.ravel()).reshape(nc, m.nv)
+        ref[:, dofs] = 0.0                                  # Dirichlet rows are masked
+        scale = np.abs(A).max() * np.abs(x).max()
+        assert np.abs(y - ref).max() <= 1e-13 * scale * 30
+
+
+# ---------------------------------------------------------------- heat solves vs oracle LU
+def _check_heat(P, dim, L, n, okw, gkw, precond):
+    ref = fo.solve_heat(dim, L, n, **okw)
+    fn = {1: P._solve_heat_1d_raw, 2: P._solve_heat_2d_raw, 3: P._solve_heat_3d_raw}[dim]
+    f = fn(*gkw["args"], **gkw["kw"], precond=precond, as_arrays=True)
+    assert f.values.shape == ref.values.shape
+    assert np.array_equal(np.asarray(f.coords), ref.coords)
+    assert np.allclose(f.times, ref.times, rtol=0, atol=1e-15)
+    for k in range(ref.values.shape[0]):
+        assert fo.rel_l2(f.values[k], ref.values[k]) <= TOL, (k, fo.rel_l2(f.values[k], ref.values[k]))
+    st = P.last_stats()
+    assert st["converged"] == 1
+    return f, st
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "gmg"])
+def test_heat_1d_config1(P, precond):
+    # BASELINE config 1: rod L=2, 100 cells, 20 / 0 Dirichlet, backward Euler (dispatcher: dt .01, 200 steps)
+    okw = dict(diffusivity=1.0, T_initial=0.0, dt=0.01, num_steps=200, T_left=20.0, T_right=0.0)
+    _check_heat(P, 1, [2.0], [100], okw,
+                dict(args=(2.0, 100, 1.0, 20.0, 0.0, 0.0, 0.01, 200), kw={}), precond)
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "gmg"])
+def test_heat_2d(P, precond):
+    okw = dict(diffusivity=1.0, T_initial=20.0, dt=0.01, num_steps=10, T_boundary=0.0)
+    _check_heat(P, 2, [1.0, 1.0], [64, 64], okw,
+                dict(args=(1.0, 1.0, 64, 64, 1.0, 0.0, 20.0, 0.01, 10), kw={}), precond)
+    okw = dict(diffusivity=0.5, T_initial=5.0, dt=0.02, num_steps=4, T_boundary=7.0, source_type="constant",
+               source_value=30.0)
+    _check_heat(P, 2, [1.0, 0.5], [30, 18], okw,
+                dict(args=(1.0, 0.5, 30, 18, 0.5, 7.0, 5.0, 0.02, 4),
+                     kw=dict(source_type="constant", source_value=30.0)), precond)
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "gmg"])
+def test_heat_3d(P, precond):
+    okw = dict(diffusivity=1.0, T_initial=20.0, dt=0.01, num_steps=5, T_boundary=0.0)
+    _, st = _check_heat(P, 3, [1, 1, 1], [32, 32, 32], okw,
+                        dict(args=(1, 1, 1, 32, 32, 32, 1.0, 0.0, 20.0, 0.01, 5), kw={}), precond)
+    if precond == "gmg":
+        assert st["levels"] >= 4 and st["iters_total"] <= 5 * 25
+    # reference defaults (10^3 cells, 20 steps) with a non-zero boundary value
+    okw = dict(diffusivity=1.0, T_initial=20.0, dt=0.01, num_steps=20, T_boundary=3.5)
+    _check_heat(P, 3, [1, 1, 1], [10, 10, 10], okw,
+                dict(args=(1, 1, 1, 10, 10, 10, 1.0, 3.5, 20.0, 0.01, 20), kw={}), precond)
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "gmg"])
+def test_heat_3d_directional_bcs_and_steady(P, precond):
+    # directional BCs (reference :606-623) leave natural (partial-patch) faces
+    for bc in (dict(T_left=10.0, T_right=1.0), dict(T_left=4.0, T_side=2.0), dict(T_side=6.0)):
+        okw = dict(diffusivity=2.0, T_initial=1.0, dt=0.05, num_steps=3, **bc)
+        _check_heat(P, 3, [1, 0.5, 0.25], [16, 8, 4], okw,
+                    dict(args=(1, 0.5, 0.25, 16, 8, 4, 2.0, 0.0, 1.0, 0.05, 3), kw=bc), precond)
+    okw = dict(diffusivity=1.5, steady=True, T_boundary=2.0, source_type="constant", source_value=50.0)
+    _check_heat(P, 3, [1, 1, 1], [16, 16, 16], okw,
+                dict(args=(1, 1, 1, 16, 16, 16, 1.5, 2.0, 0.0, 0.01, 5),
+                     kw=dict(steady=True, source_type="constant", source_value=50.0)), precond)
+    okw = dict(diffusivity=1.0, steady=True, T_left=20.0, T_right=0.0)
+    f, _ = _check_heat(P, 1, [2.0], [100], okw,
+                       dict(args=(2.0, 100, 1.0, 20.0, 0.0, 0.0, 0.01, 5), kw=dict(steady=True)), precond)
+    x = np.asarray(f.coords)[:, 0]
+    assert np.allclose(f.values[0], 20.0 * (1 - x / 2.0), atol=1e-9)   # known answer (i)
+
+
+# ---------------------------------------------------------------- elasticity vs oracle LU
+@pytest.mark.parametrize("precond", ["jacobi", "gmg"])
+@pytest.mark.parametrize("quantity", ["stress", "strain"])
+def test_elasticity_3d(P, precond, quantity):
+    ref = fo.solve_elasticity(3, [1, 0.2, 0.2], [40, 8, 8], 210e9, 0.3, body=[0, 0, -76518.0], quantity=quantity)
+    f = P._solve_elasticity_3d_static(1, 0.2, 0.2, 40, 8, 8, 210e9, 0.3, 0.0, 0.0, -76518.0, quantity,
+                                      precond=precond, as_arrays=True)
+    assert np.array_equal(f.coords, ref.coords)
+    err = fo.rel_l2(f.values[0], ref.values[0])
+    assert err <= TOL, err
+    assert P.last_stats()["converged"] == 1
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "gmg"])
+def test_elasticity_displacement_and_2d_1d(P, precond):
+    from pde_solver_b200 import solvers
+    ref = fo.solve_elasticity(3, [1, 0.3, 0.2], [16, 6, 4], 70e9, 0.33, body=[1e4, -2e4, 3e4])
+    _, val, disp = solvers._elasticity(3, [1, 0.3, 0.2], [16, 6, 4], 70e9, 0.33, [1e4, -2e4, 3e4], "stress",
+                                       precond=precond, want_displacement=True)
+    assert fo.rel_l2(disp, ref.aux["u"]) <= TOL
+    assert fo.rel_l2(val, ref.values[0]) <= TOL
+    for ps in (True, False):
+        for q in ("stress", "strain"):
+            ref = fo.solve_elasticity(2, [1, 0.5], [24, 12], 210e9, 0.3, body=[0, -76518.0], quantity=q,
+                                      plane_stress=ps)
+            f = P._solve_elasticity_2d_static(1, 0.5, 24, 12, 210e9, 0.3, 0.0, -76518.0, q, ps, precond=precond,
+                                              as_arrays=True)
+            assert fo.rel_l2(f.values[0], ref.values[0]) <= TOL, (ps, q)
+    for q in ("stress", "strain"):
+        ref = fo.solve_elasticity(1, [1.5], [64], 210e9, body=[1e6], quantity=q, area=2.0)
+        f = P._solve_elasticity_1d_static(1.5, 64, 210e9, 2.0, 1e6, q, precond=precond, as_arrays=True)
+        assert fo.rel_l2(f.values[0], ref.values[0]) <= TOL, q
+
+
+def test_zero_body_force_gives_zero_field(P):
+    f = P._solve_elasticity_3d_static(1, 1, 1, 8, 8, 8, 210e9, 0.3, as_arrays=True)    # docstring :2639-2642
+    assert np.all(f.values == 0.0)
+
+
+# ---------------------------------------------------------------- larger sizes: manufactured solutions
+@pytest.mark.parametrize("kind,n,precond", [("heat", [128, 128, 128], "gmg"), ("heat", [96, 80, 64], "jacobi"),
+                                            ("elasticity", [128, 32, 32], "gmg")])
+def test_manufactured_solution_large(P, ctx, kind, n, precond):
+    # (iv-c): b = A u* with the (small-size validated) GPU operator, solve, compare with u*
+    L = [1.0, 1.0, 1.0] if kind == "heat" else [1.0, 0.25, 0.25]
+    lam, mu = fo.lame(210e9, 0.3, 3)
+    faces = {f: 0.0 for f in range(6)} if kind == "heat" else {0: 0.0}
+    p = P._lib.op_params(kind, 3, n, L, 1.0, 0.01, lam, mu, bc=P._lib.make_bc(faces))
+    nv, _ = P._lib.mesh_counts(3, n)
+    nc = 3 if kind == "elasticity" else 1
+    X = P.mesh.coordinates(3, n, L)
+    mask, _ = P.mesh.dirichlet(3, n, P._lib.make_bc(faces))
+    us = np.stack([np.sin(3 * X[:, 0] + c) * np.cos(2 * X[:, 1]) * (1 + X[:, 2]) for c in range(nc)])
+    us[:, mask == 1] = 0.0
+    b = P._lib.op_apply(ctx, p, us)
+    x, st = P._lib.op_solve(ctx, p, b, P._lib.make_opts(rtol=1e-11, precond=precond))
+    assert st["converged"] == 1 and st["true_relres"] < 1e-9
+    assert fo.rel_l2(x, us) <= TOL, fo.rel_l2(x, us)
