@@ -27,9 +27,10 @@ extern "C" int pde_ctx_create(int device, pde_ctx** out) {
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming));
   CUDA_OK(cudaMalloc(&c->red.partials, sizeof(double) * RED_MAX_BLOCKS * RED_MAX_VALS));
   CUDA_OK(cudaMalloc(&c->red.counter, sizeof(unsigned)));
-  CUDA_OK(cudaMemset(c->red.counter, 0, sizeof(unsigned)));
+  CUDA_OK(cudaMemsetAsync(c->red.counter, 0, sizeof(unsigned), c->stream));
   CUDA_OK(cudaMalloc(&c->scal, sizeof(double) * S_NSLOTS));
-  CUDA_OK(cudaMemset(c->scal, 0, sizeof(double) * S_NSLOTS));
+  CUDA_OK(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_NSLOTS, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
   CUDA_OK(cudaHostAlloc(&c->h_scal, sizeof(double) * S_NSLOTS, cudaHostAllocDefault));
   *out = c;
   return 0;
@@ -213,9 +214,9 @@ extern "C" int pde_heat_open(pde_ctx* c, const pde_heat_params* p, const pde_sol
     if ((rc = s->A.setup_scalar(c, s->g, s->bc, alpha, beta))) break;
     if ((rc = s->K.setup_scalar(c, s->g, s->bc, 0.0, 1.0))) break;
     if ((rc = s->M.setup_scalar(c, s->g, s->bc, 1.0, 0.0))) break;
-    if ((rc = s->u.alloc(s->g, 1))) break;
-    if ((rc = s->r.alloc(s->g, 1))) break;
-    if ((rc = s->w.alloc(s->g, 1))) break;
+    if ((rc = s->u.alloc(c, s->g, 1))) break;
+    if ((rc = s->r.alloc(c, s->g, 1))) break;
+    if ((rc = s->w.alloc(c, s->g, 1))) break;
     s->nloc = (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzl;
     if ((rc = s->dense.alloc(sizeof(double) * s->nloc))) break;
     long long ndofs = (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzg;
@@ -397,8 +398,8 @@ extern "C" int pde_op_apply(pde_ctx* c, const pde_op_params* p, const double* x,
   int nc;
   PDE_OK(setup_op(c, p, &G.A, &nc));
   const Grid& g = G.A.g;
-  PDE_OK(G.x.alloc(g, nc));
-  PDE_OK(G.y.alloc(g, nc));
+  PDE_OK(G.x.alloc(c, g, nc));
+  PDE_OK(G.y.alloc(c, g, nc));
   const long long nloc = (long long)g.nn[0] * g.nn[1] * g.nzl;
   DevMem dense;
   PDE_OK(dense.alloc(sizeof(double) * nloc * nc));
@@ -434,8 +435,8 @@ extern "C" int pde_op_bench(pde_ctx* c, const pde_op_params* p, int reps, int wa
   int nc;
   PDE_OK(setup_op(c, p, &G.A, &nc));
   const Grid& g = G.A.g;
-  PDE_OK(G.x.alloc(g, nc));
-  PDE_OK(G.y.alloc(g, nc));
+  PDE_OK(G.x.alloc(c, g, nc));
+  PDE_OK(G.y.alloc(c, g, nc));
   RowLaunch rl = row_launch(c, g);
   k_fill_pattern<<<rl.grid, rl.block, 0, c->stream>>>(g, nc, G.x.p);
   c->launches++;
@@ -467,7 +468,7 @@ static int solve_with(pde_ctx* c, OpGuard& G, const pde_op_params* p, const pde_
     G.mg.ratio = o.cheby_ratio > 1 ? o.cheby_ratio : 8.0;
     use_mg = choose_precond(o, c, ndofs, G.mg) == PDE_PRECOND_GMG;
   }
-  PDE_OK(G.w.alloc(G.A.g, nc));
+  PDE_OK(G.w.alloc(c, G.A.g, nc));
   return pcg_solve(c, G.A, use_mg ? &G.mg : nullptr, G.w, x, r, bn2, o, st);
 }
 
@@ -481,9 +482,9 @@ extern "C" int pde_op_solve(pde_ctx* c, const pde_op_params* p, const pde_solver
   int nc;
   PDE_OK(setup_op(c, p, &G.A, &nc));
   const Grid& g = G.A.g;
-  PDE_OK(G.x.alloc(g, nc));
-  PDE_OK(G.y.alloc(g, nc));  // holds b
-  PDE_OK(G.r.alloc(g, nc));
+  PDE_OK(G.x.alloc(c, g, nc));
+  PDE_OK(G.y.alloc(c, g, nc));  // holds b
+  PDE_OK(G.r.alloc(c, g, nc));
   const long long nloc = (long long)g.nn[0] * g.nn[1] * g.nzl;
   DevMem dense;
   PDE_OK(dense.alloc(sizeof(double) * nloc * nc));
@@ -554,8 +555,8 @@ extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const
   int nc;
   PDE_OK(setup_op(c, &op, &G.A, &nc));
   const Grid& g = G.A.g;
-  PDE_OK(G.x.alloc(g, nc));
-  PDE_OK(G.r.alloc(g, nc));
+  PDE_OK(G.x.alloc(c, g, nc));
+  PDE_OK(G.r.alloc(c, g, nc));
   const long long nloc = (long long)g.nn[0] * g.nn[1] * g.nzl;
   pde_stats st;
   stats_init(&st, nloc * nc);
@@ -584,8 +585,8 @@ extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const
   std::memset(&mp.bc, 0, sizeof(mp.bc));
   int nc1;
   PDE_OK(setup_op(c, &mp, &P.A, &nc1));
-  PDE_OK(P.x.alloc(g, 1));
-  PDE_OK(P.r.alloc(g, 1));
+  PDE_OK(P.x.alloc(c, g, 1));
+  PDE_OK(P.r.alloc(c, g, 1));
   pde_stats sp;
   stats_init(&sp, nloc);
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));

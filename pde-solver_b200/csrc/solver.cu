@@ -4,6 +4,8 @@
 // (fenics_mcp_server.py:265,311,397,440,661,709,1538,1688,1838: assemble AIJ + sparse LU every call)
 // with a matrix-free preconditioned CG whose operator is never stored.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "solver.cuh"
@@ -21,12 +23,16 @@ int launch_stencil(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, 
 }
 
 // ---- Field ---------------------------------------------------------------------------------
-int Field::alloc(const Grid& g, int ncomp) {
+int Field::alloc(pde_ctx* c, const Grid& g, int ncomp) {
   release();
-  bytes = (size_t)g.comp_stride * ncomp * sizeof(double);
+  // lead/tail pad: the (-1,-1,-1) neighbour of node (0,0,0) lies PX+1 elements before the ghost plane
+  const size_t lead = (((size_t)g.PX + 1 + 31) / 32) * 32;
+  bytes = ((size_t)g.comp_stride * ncomp + 2 * lead) * sizeof(double);
   CUDA_OK(cudaMalloc(&raw, bytes));
-  CUDA_OK(cudaMemset(raw, 0, bytes));
-  p = raw + g.plane;
+  // zero on the context's stream: it is a non-blocking stream, so a legacy-stream cudaMemset would
+  // not be ordered against the kernels that use this field
+  CUDA_OK(cudaMemsetAsync(raw, 0, bytes, c->stream));
+  p = raw + lead + g.plane;
   return 0;
 }
 void Field::release() {
@@ -37,7 +43,6 @@ void Field::release() {
 
 // ---- Operator --------------------------------------------------------------------------------
 int Operator::upload(pde_ctx* c) {
-  (void)c;
   const int nc = tab.ncomp, nn = nc * nc;
   dev.ncomp = nc;
   dev.gershgorin = tab.gershgorin;
@@ -52,9 +57,10 @@ int Operator::upload(pde_ctx* c) {
   CUDA_OK(cudaMalloc(&dev.coef, tab.coef.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&dev.dinv, dinv.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&dev.load, PDE_NCLASS * sizeof(double)));
-  CUDA_OK(cudaMemcpy(dev.coef, tab.coef.data(), tab.coef.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(dev.dinv, dinv.data(), dinv.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(dev.load, tab.load.data(), PDE_NCLASS * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpyAsync(dev.coef, tab.coef.data(), tab.coef.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(dev.dinv, dinv.data(), dinv.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(dev.load, tab.load.data(), PDE_NCLASS * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));  // host staging vectors die at return
   return 0;
 }
 int Operator::setup_scalar(pde_ctx* c, const Grid& g_, const BcDev& bc_, double alpha, double beta) {
@@ -138,7 +144,7 @@ static int dense_inverse_spd(std::vector<double>& A, int n) {
   return 0;
 }
 
-static int build_dense_coarse(MGLevel& L) {
+static int build_dense_coarse(pde_ctx* c, MGLevel& L) {
   const Grid& g = L.op.g;
   const int nc = L.op.tab.ncomp, nn = nc * nc;
   std::vector<long long> idx;
@@ -165,8 +171,9 @@ static int build_dense_coarse(MGLevel& L) {
   L.n_dense = (int)n;
   CUDA_OK(cudaMalloc(&L.Ainv, A.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&L.idx, idx.size() * sizeof(long long)));
-  CUDA_OK(cudaMemcpy(L.Ainv, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(L.idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpyAsync(L.Ainv, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaMemcpyAsync(L.idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+  CUDA_OK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -188,14 +195,15 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
     PDE_OK(make_grid(dim, n, Lu, c->rank, c->world, &g));
     if (kind == PDE_OP_ELASTICITY) PDE_OK(L->op.setup_elasticity(c, g, fine.bc, p0, p1));
     else PDE_OK(L->op.setup_scalar(c, g, fine.bc, p0, p1));
-    PDE_OK(L->xa.alloc(g, ncomp));
-    PDE_OK(L->xb.alloc(g, ncomp));
-    PDE_OK(L->d.alloc(g, ncomp));
-    PDE_OK(L->r.alloc(g, ncomp));
-    if (level > 0) PDE_OK(L->b.alloc(g, ncomp));
+    PDE_OK(L->xa.alloc(c, g, ncomp));
+    PDE_OK(L->xb.alloc(c, g, ncomp));
+    PDE_OK(L->d.alloc(c, g, ncomp));
+    PDE_OK(L->r.alloc(c, g, ncomp));
+    if (level > 0) PDE_OK(L->b.alloc(c, g, ncomp));
     lv.push_back(std::move(L));
     // can we coarsen further?
     bool can = c->world == 1;
+    if (const char* ml = getenv("PDE_B200_MAX_LEVELS")) can = can && (level + 1 < atoi(ml));
     int32_t nc2[3] = {0, 0, 0};
     for (int q = 0; q < nax; ++q) {
       if (n[q] % 2 != 0 || n[q] < 2) can = false;
@@ -218,7 +226,7 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
   long long nodes = (long long)Lc.op.g.nn[0] * Lc.op.g.nn[1] * Lc.op.g.nzl;
   if (lv.size() > 1 && nodes * ncomp <= 4 * PDE_DENSE_MAX) {
     long long nfree = count_free_and_index(Lc.op.g, Lc.op.bc, ncomp, nullptr, nullptr);
-    if (nfree > 0 && nfree <= PDE_DENSE_MAX) PDE_OK(build_dense_coarse(Lc));
+    if (nfree > 0 && nfree <= PDE_DENSE_MAX) PDE_OK(build_dense_coarse(c, Lc));
   }
   return 0;
 }
@@ -317,9 +325,9 @@ int choose_precond(const pde_solver_opts& o, pde_ctx* c, long long ndofs, const 
 }
 
 // ---- PCG -----------------------------------------------------------------------------------------
-int PcgWork::alloc(const Grid& g, int ncomp) {
-  PDE_OK(p.alloc(g, ncomp));
-  PDE_OK(q.alloc(g, ncomp));
+int PcgWork::alloc(pde_ctx* c, const Grid& g, int ncomp) {
+  PDE_OK(p.alloc(c, g, ncomp));
+  PDE_OK(q.alloc(c, g, ncomp));
   return 0;
 }
 void PcgWork::release() { p.release(); q.release(); }
@@ -351,6 +359,13 @@ int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* 
     PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, z, S_RHO0, S_RHO0, 1, 0));
   }
   PDE_OK(read_scal(c, S_RHO0 + 1, 1, &rr));
+  const bool trace = getenv("PDE_B200_TRACE") != nullptr;
+  if (trace) {
+    double v[2];
+    PDE_OK(read_scal(c, S_RHO0, 2, v));
+    fprintf(stderr, "[pcg] n=%lld gmg=%d levels=%d bnorm2=%.6e rho0=%.6e rr0=%.6e\n", (long long)g.total, (int)gmg,
+            gmg ? mg->levels() : 1, bnorm2, v[0], v[1]);
+  }
   int it = 0;
   bool conv = rr <= tol2;
   const int check = gmg ? 1 : (o.check_every > 0 ? o.check_every : 10);
@@ -370,6 +385,12 @@ int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* 
     }
     PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, gmg ? z : r, sr, sn, 0, !gmg));
     ++it;
+    if (trace && (it <= 30 || it % 50 == 0)) {
+      double v[2], pap;
+      PDE_OK(read_scal(c, sn, 2, v));
+      PDE_OK(read_scal(c, S_XY, 1, &pap));
+      fprintf(stderr, "[pcg] it=%d pAp=%.6e rho=%.6e rr=%.6e\n", it, pap, v[0], v[1]);
+    }
     if (it % check == 0 || it >= o.max_iters) {
       PDE_OK(read_scal(c, sn + 1, 1, &rr));
       if (!(rr == rr)) PDE_FAIL("PCG broke down (NaN residual)");

@@ -8,7 +8,7 @@ struct Field {
   double* raw = nullptr;  // allocation start (ghost plane of component 0)
   double* p = nullptr;    // plane 0 of component 0
   size_t bytes = 0;
-  int alloc(const Grid& g, int ncomp);
+  int alloc(pde_ctx* c, const Grid& g, int ncomp);
   void release();
 };
 
@@ -47,7 +47,7 @@ struct Hierarchy {
 
 struct PcgWork {
   Field p, q;
-  int alloc(const Grid& g, int ncomp);
+  int alloc(pde_ctx* c, const Grid& g, int ncomp);
   void release();
 };
 
