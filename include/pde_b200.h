@@ -39,6 +39,10 @@ int pde_ctx_sync(pde_ctx* ctx);
 int pde_timer_start(pde_ctx* ctx);
 int pde_timer_stop(pde_ctx* ctx, double* elapsed_ms);
 
+/* pinned host memory for the host<->device legs of a step (cudaHostAlloc / cudaFreeHost) */
+int pde_host_alloc(uint64_t bytes, void** out);
+int pde_host_free(void* p);
+
 /* ---- multi-GPU: slab partition along the slowest axis, NCCL over NVLink ------------- */
 /* libnccl.so.2 is dlopen()ed from `libnccl_path` (NULL: default search path). */
 int pde_nccl_unique_id(const char* libnccl_path, void* id128 /* 128 bytes out */);

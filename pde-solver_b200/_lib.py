@@ -83,7 +83,7 @@ def lib():
                      "pde_mesh_cells", "pde_dofmap_cells", "pde_boundary_mask", "pde_heat_solve",
                      "pde_heat_open", "pde_heat_set_state", "pde_heat_step", "pde_heat_get_state",
                      "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench",
-                     "pde_op_solve", "pde_version"):
+                     "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -243,3 +243,60 @@ def op_bench(ctx, p, reps=20, warmup=3):
     ms, nd = C.c_double(), C.c_int64()
     check(lib().pde_op_bench(ctx.handle, C.byref(p), int(reps), int(warmup), C.byref(ms), C.byref(nd)))
     return ms.value, nd.value
+
+
+class PinnedArray:
+    """float64 NumPy view over cudaHostAlloc'ed memory (for the H2D/D2H legs of a step)."""
+
+    def __init__(self, n):
+        self.ptr = C.c_void_p()
+        check(lib().pde_host_alloc(C.c_uint64(int(n) * 8), C.byref(self.ptr)))
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_double)), shape=(int(n),))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().pde_host_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+class HeatStepper:
+    """Device-resident backward-Euler stepper (pde_heat_open/step/close): state stays in HBM."""
+
+    def __init__(self, ctx, dim, n, L, diffusivity, dt, T_initial=0.0, bc=None, source_value=0.0, steady=False,
+                 opts=None):
+        p = HeatParams()
+        p.dim = int(dim)
+        p.n = i3(n)
+        p.L = d3(L)
+        p.diffusivity = float(diffusivity)
+        p.dt = float(dt)
+        p.num_steps = 0
+        p.steady = 1 if steady else 0
+        p.source_value = float(source_value)
+        p.initial_type = IC["constant"]
+        p.snapshot_stride = 1
+        p.T_initial = float(T_initial)
+        p.bc = bc if bc is not None else Bc()
+        self.ctx = ctx
+        self.handle = C.c_void_p()
+        o = opts if opts is not None else make_opts()
+        check(lib().pde_heat_open(ctx.handle, C.byref(p), C.byref(o), C.byref(self.handle)))
+        self.nloc = int(lib().pde_heat_local_nverts(self.handle))
+
+    def step(self, nsteps=1):
+        st = Stats()
+        check(lib().pde_heat_step(self.handle, int(nsteps), C.byref(st)))
+        return st.as_dict()
+
+    def set_state(self, u):
+        check(lib().pde_heat_set_state(self.handle, ptr(u)))
+
+    def get_state(self, out):
+        check(lib().pde_heat_get_state(self.handle, ptr(out)))
+        return out
+
+    def close(self):
+        if self.handle:
+            lib().pde_heat_close(self.handle)
+            self.handle = C.c_void_p()

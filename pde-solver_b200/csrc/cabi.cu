@@ -71,6 +71,16 @@ extern "C" int pde_timer_stop(pde_ctx* c, double* ms) {
   return 0;
 }
 
+extern "C" int pde_host_alloc(uint64_t bytes, void** out) {
+  if (!out) PDE_FAIL("null out pointer");
+  CUDA_OK(cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocDefault));
+  return 0;
+}
+extern "C" int pde_host_free(void* p) {
+  if (p) CUDA_OK(cudaFreeHost(p));
+  return 0;
+}
+
 struct DevMem {
   void* p = nullptr;
   ~DevMem() { if (p) cudaFree(p); }
