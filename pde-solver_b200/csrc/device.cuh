@@ -2,7 +2,7 @@
 #pragma once
 #include "common.h"
 
-#define RED_MAX_BLOCKS 4096
+#define RED_MAX_BLOCKS 65536
 #define RED_MAX_VALS 4
 
 // scalar slots (device doubles) used by the PCG recurrences
@@ -64,6 +64,63 @@ __device__ __forceinline__ long long kOffDdev(int k, int PX, long long plane) {
   return D[k][0] + (long long)PX * D[k][1] + plane * D[k][2];
 }
 
+// ----------------------------------------------------------------------------------------------
+// deterministic two-stage reduction: per-block partials, last block sums them in fixed order
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+template <int NV>
+__device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], ReduceBuf red, double* out) {
+  __shared__ double sm[NV][32];
+  __shared__ bool is_last;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nth = blockDim.x * blockDim.y;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = (nth + 31) >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (lane == 0) sm[i][warp] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = lane < nwarp ? sm[i][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+      if (lane == 0) red.partials[(size_t)blockIdx.x * RED_MAX_VALS + i] = s;
+    }
+    if (lane == 0) {
+      __threadfence();
+      unsigned t = atomicAdd(red.counter, 1u);
+      is_last = (t == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = 0.0;
+    for (unsigned b = tid; b < gridDim.x; b += nth) s += red.partials[(size_t)b * RED_MAX_VALS + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if (lane == 0) sm[i][warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double t = lane < nwarp ? sm[i][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+      if (lane == 0) out[i] = t;
+    }
+  }
+  if (tid == 0) *red.counter = 0u;
+}
+
+#endif  // __CUDACC__
+
 // ---- launch geometry for row-structured kernels -----------------------------------------
 struct RowLaunch {
   dim3 block, grid;
@@ -98,6 +155,8 @@ struct OpDev {
   double* dinv = nullptr;   // [27][nc]
   double* load = nullptr;   // [27]
   double h_int[PDE_NOFF * 9];  // interior class coefficients (host copy, passed as kernel params)
+  double h_dinv_int[3] = {0, 0, 0};  // interior class Jacobi diagonal inverse
+  double h_load_int = 0;             // interior class load (integral of the hat function)
   double gershgorin = 0;
 };
 

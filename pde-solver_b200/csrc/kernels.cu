@@ -11,60 +11,6 @@
 #include "device.cuh"
 
 // ----------------------------------------------------------------------------------------------
-// deterministic two-stage reduction: per-block partials, last block sums them in fixed order
-// ----------------------------------------------------------------------------------------------
-template <int NV>
-__device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], ReduceBuf red, double* out) {
-  __shared__ double sm[NV][32];
-  __shared__ bool is_last;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int nth = blockDim.x * blockDim.y;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = (nth + 31) >> 5;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    double s = v[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) sm[i][warp] = s;
-  }
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      double s = lane < nwarp ? sm[i][lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-      if (lane == 0) red.partials[(size_t)blockIdx.x * RED_MAX_VALS + i] = s;
-    }
-    if (lane == 0) {
-      __threadfence();
-      unsigned t = atomicAdd(red.counter, 1u);
-      is_last = (t == gridDim.x - 1);
-    }
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    double s = 0.0;
-    for (unsigned b = tid; b < gridDim.x; b += nth) s += red.partials[(size_t)b * RED_MAX_VALS + i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    __syncthreads();
-    if (lane == 0) sm[i][warp] = s;
-    __syncthreads();
-    if (warp == 0) {
-      double t = lane < nwarp ? sm[i][lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-      if (lane == 0) out[i] = t;
-    }
-  }
-  if (tid == 0) *red.counter = 0u;
-}
-
-// ----------------------------------------------------------------------------------------------
 // generic stencil kernel
 // ----------------------------------------------------------------------------------------------
 template <int NC>

@@ -54,6 +54,8 @@ int Operator::upload(pde_ctx* c) {
     }
   for (int k = 0; k < PDE_NOFF; ++k)
     for (int q = 0; q < nn; ++q) dev.h_int[k * nn + q] = tab.coef[((size_t)13 * PDE_NOFF + k) * nn + q];
+  for (int i = 0; i < nc; ++i) dev.h_dinv_int[i] = dinv[13 * nc + i];
+  dev.h_load_int = tab.load[13];
   CUDA_OK(cudaMalloc(&dev.coef, tab.coef.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&dev.dinv, dinv.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&dev.load, PDE_NCLASS * sizeof(double)));

@@ -1,11 +1,493 @@
 // Specialised streaming kernels for the 3D hot paths (heat / mass 15-point, elasticity 3x3-block).
 // launch_stencil_fast() claims a launch when a specialised kernel applies; otherwise the generic
 // table kernel in kernels.cu runs.
+//
+// k_sweep3d: TMA-fed plane sweep.
+//   A CTA owns an (x,y) tile of TX x TY nodes and marches over a chunk of z planes.  One elected
+//   thread streams each (TX+4) x (TY+2) plane tile (halo included, out-of-domain elements zero-filled
+//   by the TMA unit) into a ring of shared-memory stages with cp.async.bulk.tensor, completion on an
+//   mbarrier.  The Kuhn 15-point stencil splits by plane into a 4-point part seen from the plane above
+//   (dz=-1), a 7-point in-plane part and a 4-point part seen from the plane below (dz=+1), so every
+//   plane is read from shared memory ONCE: while plane q is resident each thread adds its contribution
+//   to the three outputs q-1, q, q+1 it keeps in registers, then retires output q-1.  A thread owns a
+//   strip of YS nodes along y, which cuts shared-memory reads to (3*YS+4)/YS values per output.
+//   Algorithmic HBM traffic: read x once, write y once (16 B/dof; Chebyshev sweep 40 B/dof).
+//   Nodes whose element patch is incomplete (natural / traction-free faces) are recomputed from the
+//   27-class table when they retire; Dirichlet rows are masked.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+
 #include "device.cuh"
+
+#define SW_STAGES 4
+
+struct SweepGeom {
+  int tx, ty;         // tile size in nodes
+  int bx, by;         // TMA box = (tx+4, ty+2), origin (x0-2, y0-1)
+  int ntx, nty, nzc;  // tiles / z-chunks
+  int zc;             // planes per chunk
+  int ns;             // strips (of YS rows) per tile
+  int stage_elems;    // doubles per stage (all components), multiple of 16
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
+template <int NC>
+struct Coef {
+  double c[PDE_NOFF][NC * NC];
+};
+
+struct SweepArgs {
+  const double* x;
+  const double* b;
+  double* y;
+  double* d;
+  double bconst[3];
+  double bscale, ascale, c1, c2;
+  double load_int;    // load of the interior class
+  double dinv_int[3]; // Jacobi diagonal inverse of the interior class
+  int do_reduce;
+};
+
+// acc[i] += sum_j C[k][i][j] * v[j]
+template <int NC>
+__device__ __forceinline__ void blk_fma(double (&acc)[NC], const Coef<NC>& C, int k, const double (&v)[NC]) {
+#pragma unroll
+  for (int i = 0; i < NC; ++i)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[i] = fma(C.c[k][i * NC + j], v[j], acc[i]);
+}
+template <int NC>
+__device__ __forceinline__ void blk_set(double (&acc)[NC], const Coef<NC>& C, int k, const double (&v)[NC]) {
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    acc[i] = C.c[k][i * NC] * v[0];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) acc[i] = fma(C.c[k][i * NC + j], v[j], acc[i]);
+  }
+}
+
+// One resident plane: V[r][c] = plane values at strip rows r-1 (r = 0..YS+1), columns c-1 (c = 0..2).
+//   aP (output one plane below) gets the dz=+1 part, a0 the in-plane part, aM (output one plane above)
+//   is started with the dz=-1 part.
+template <int NC, int YS>
+__device__ __forceinline__ void plane_contrib(const Coef<NC>& C, const double (&V)[YS + 2][3][NC],
+                                              double (&aP)[YS][NC], double (&a0)[YS][NC], double (&aM)[YS][NC]) {
+#pragma unroll
+  for (int j = 0; j < YS; ++j) {
+    const int r = j + 1;
+    // in-plane: centre, +x, -x, +y, -y, (+x,+y), (-x,-y)
+    blk_fma<NC>(a0[j], C, 0, V[r][1]);
+    blk_fma<NC>(a0[j], C, 1, V[r][2]);
+    blk_fma<NC>(a0[j], C, 2, V[r][0]);
+    blk_fma<NC>(a0[j], C, 3, V[r + 1][1]);
+    blk_fma<NC>(a0[j], C, 4, V[r - 1][1]);
+    blk_fma<NC>(a0[j], C, 7, V[r + 1][2]);
+    blk_fma<NC>(a0[j], C, 8, V[r - 1][0]);
+    // this plane is dz=+1 for the output below: (0,0,1), (1,0,1), (0,1,1), (1,1,1)
+    blk_fma<NC>(aP[j], C, 5, V[r][1]);
+    blk_fma<NC>(aP[j], C, 9, V[r][2]);
+    blk_fma<NC>(aP[j], C, 11, V[r + 1][1]);
+    blk_fma<NC>(aP[j], C, 13, V[r + 1][2]);
+    // this plane is dz=-1 for the output above: (0,0,-1), (-1,0,-1), (0,-1,-1), (-1,-1,-1)
+    blk_set<NC>(aM[j], C, 6, V[r][1]);
+    blk_fma<NC>(aM[j], C, 10, V[r][0]);
+    blk_fma<NC>(aM[j], C, 12, V[r - 1][1]);
+    blk_fma<NC>(aM[j], C, 14, V[r - 1][0]);
+  }
+}
+
+// Row of a node whose element patch is incomplete (natural / traction-free faces): recomputed from the
+// 27-class table with global loads.  Rare (domain faces only), kept out of line to protect registers.
+template <int NC>
+__device__ __noinline__ void slow_row(const Grid& g, const double* __restrict__ coef, const double* __restrict__ x,
+                                      long long idx, int cls, double* acc) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+  for (int k = 0; k < PDE_NOFF; ++k) {
+    const double* cf = coef + ((size_t)cls * PDE_NOFF + k) * (NC * NC);
+    const long long off = g.koff[k];
+    double xv[NC];
+#pragma unroll
+    for (int q = 0; q < NC; ++q) xv[q] = x[idx + off + q * g.comp_stride];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int q = 0; q < NC; ++q) acc[c] = fma(__ldg(cf + c * NC + q), xv[q], acc[c]);
+  }
+}
+
+template <int NC, int YS, bool CHEBY, bool HAS_B>
+__global__ void __launch_bounds__(NC == 1 ? 384 : 256)
+k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
+          const __grid_constant__ Coef<NC> C, const double* __restrict__ coef, const double* __restrict__ dinv,
+          const double* __restrict__ load, const __grid_constant__ SweepArgs a, const __grid_constant__ SweepGeom sw,
+          ReduceBuf red, double* red_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage0 = reinterpret_cast<double*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SW_STAGES * sw.stage_elems * sizeof(double));
+
+  const int t = threadIdx.x;
+  const int item = blockIdx.x;
+  const int itx = item % sw.ntx;
+  const int ity = (item / sw.ntx) % sw.nty;
+  const int izc = item / (sw.ntx * sw.nty);
+  const int x0 = itx * sw.tx, y0 = ity * sw.ty;
+  const int za = izc * sw.zc;
+  const int zb = min(za + sw.zc, g.nzl);
+  const int nplanes = zb - za + 2;  // planes za-1 .. zb
+  const uint32_t stage_bytes = (uint32_t)(sw.bx * sw.by * NC * sizeof(double));
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t stg0 = smem_u32(stage0);
+  const uint32_t stage_stride = (uint32_t)(sw.stage_elems * sizeof(double));
+
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < SW_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0) {
+    for (int i = 0; i < SW_STAGES && i < nplanes; ++i) {
+      mbar_expect_tx(bar0 + 8 * i, stage_bytes);
+      // tensor z coordinate: ghost plane is z=0, local plane lz is z=lz+1.  The box starts at x0-2: TMA
+      // needs the inner start coordinate 16-byte aligned (even for FP64); x0-1 raises an illegal-instruction fault
+      tma_load_4d(stg0 + i * stage_stride, &tmx, x0 - 2, y0 - 1, za + i, 0, bar0 + 8 * i);
+    }
+  }
+
+  const int lx = t % sw.tx;
+  const int st = t / sw.tx;
+  const bool active = st < sw.ns;
+  const int ix = x0 + lx;
+  const int iy0 = y0 + st * YS;
+  const int comp_elems = sw.bx * sw.by;
+  // smem offset of V[0][0]: box row st*YS (= y -1), box column lx+1 (= x -1)
+  const double* sbase = stage0 + (st * YS) * sw.bx + lx + 1;
+
+  // per-thread masks, constant over the z march: bit j describes node (ix, iy0+j)
+  unsigned valid = 0, dirxy = 0, slowxy = 0;
+  bool z_excl = false;  // "other_faces" predicate: side faces skip the x-end columns
+  if (active && ix < g.nn[0]) {
+    const bool xe0 = ix == 0, xe1 = ix == g.nn[0] - 1;
+    z_excl = bc.side_excl && (xe0 || xe1);
+#pragma unroll
+    for (int j = 0; j < YS; ++j) {
+      const int iy = iy0 + j;
+      if (iy >= g.nn[1]) continue;
+      valid |= 1u << j;
+      const bool ye0 = iy == 0, ye1 = iy == g.nn[1] - 1;
+      bool d = (xe0 && bc.on[0]) || (xe1 && bc.on[1]);
+      if (!d && !z_excl) d = (ye0 && bc.on[2]) || (ye1 && bc.on[3]);
+      if (d) dirxy |= 1u << j;
+      if (xe0 || xe1 || ye0 || ye1) slowxy |= 1u << j;
+    }
+  }
+  const long long col0 = (long long)g.PX * iy0 + ix;  // flat offset of (ix, iy0) inside a plane
+
+  double accA[YS][NC], accB[YS][NC], accC[YS][NC];
+  double xq[YS][NC];  // own-column values of the plane read one step earlier (the one that retires next)
+#pragma unroll
+  for (int j = 0; j < YS; ++j)
+#pragma unroll
+    for (int i = 0; i < NC; ++i) accA[j][i] = accB[j][i] = accC[j][i] = xq[j][i] = 0.0;
+  double red_xy = 0.0, red_yy = 0.0;
+
+  // One pipeline step: plane q = za-1+i is resident in stage i%STAGES; output plane q-1 retires.
+  auto body = [&](int i, double (&aP)[YS][NC], double (&a0)[YS][NC], double (&aM)[YS][NC]) {
+    const int stage = i % SW_STAGES;
+    const uint32_t parity = (uint32_t)((i / SW_STAGES) & 1);
+    const int zout = za + i - 2;
+    const bool fin = (i >= 2) && valid;
+    const long long obase = (long long)g.plane * zout + col0;
+    // early global loads for the retiring outputs (consumed after the stencil arithmetic)
+    double bv[YS][NC], dv[YS][NC];
+    if (fin && (HAS_B || CHEBY)) {
+#pragma unroll
+      for (int j = 0; j < YS; ++j)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const long long ii = obase + (long long)g.PX * j + c * g.comp_stride;
+          const bool ok = (valid >> j) & 1u;
+          if (HAS_B) bv[j][c] = ok ? a.b[ii] : 0.0;
+          if (CHEBY) dv[j][c] = ok ? a.d[ii] : 0.0;
+        }
+    }
+    mbar_wait(bar0 + 8 * stage, parity);
+    double xc[YS][NC];
+    if (active) {
+      double V[YS + 2][3][NC];
+      const double* sp = sbase + (size_t)stage * sw.stage_elems;
+#pragma unroll
+      for (int r = 0; r < YS + 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if ((r == 0 && c == 2) || (r == YS + 1 && c == 0)) {
+#pragma unroll
+            for (int q = 0; q < NC; ++q) V[r][c][q] = 0.0;  // never used
+          } else {
+#pragma unroll
+            for (int q = 0; q < NC; ++q) V[r][c][q] = sp[q * comp_elems + r * sw.bx + c];
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < YS; ++j)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) xc[j][q] = V[j + 1][1][q];
+      plane_contrib<NC, YS>(C, V, aP, a0, aM);
+    }
+    __syncthreads();  // every thread has consumed this stage
+    if (t == 0 && i + SW_STAGES < nplanes) {
+      mbar_expect_tx(bar0 + 8 * stage, stage_bytes);
+      tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i + SW_STAGES, 0, bar0 + 8 * stage);
+    }
+    if (fin) {
+      const int gz = zout + g.z0;
+      const bool ze0 = g.nc[2] > 0 && gz == 0, ze1 = g.nc[2] > 0 && gz == g.nzg - 1;
+      const bool zslow = ze0 || ze1;
+      const bool zdir = !z_excl && ((ze0 && bc.on[4]) || (ze1 && bc.on[5]));
+#pragma unroll
+      for (int j = 0; j < YS; ++j) {
+        if (!((valid >> j) & 1u)) continue;
+        const long long idx = obase + (long long)g.PX * j;
+        if (((dirxy >> j) & 1u) || zdir) {  // Dirichlet row: masked
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            const long long ii = idx + c * g.comp_stride;
+            if (CHEBY) { a.d[ii] = 0.0; a.y[ii] = xq[j][c]; }
+            else if (a.y) a.y[ii] = 0.0;
+          }
+          continue;
+        }
+        double acc[NC], di[NC], ld;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { acc[c] = aP[j][c]; di[c] = a.dinv_int[c]; }
+        ld = a.load_int;
+        if (((slowxy >> j) & 1u) || zslow) {  // incomplete element patch: class-table row (domain faces only)
+          const int iy = iy0 + j;
+          const int cls = node_class(g, ix, iy, gz);
+          slow_row<NC>(g, coef, a.x, idx, cls, acc);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) di[c] = __ldg(dinv + cls * NC + c);
+          ld = __ldg(load + cls);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const long long ii = idx + c * g.comp_stride;
+          const double B = HAS_B ? bv[j][c] : a.bconst[c] * ld;
+          if (CHEBY) {
+            const double dn = a.c1 * dv[j][c] + a.c2 * di[c] * (B - acc[c]);
+            a.d[ii] = dn;
+            a.y[ii] = xq[j][c] + dn;
+          } else {
+            const double yv = a.bscale * B + a.ascale * acc[c];
+            if (a.y) a.y[ii] = yv;
+            red_xy = fma(xq[j][c], yv, red_xy);
+            red_yy = fma(yv, yv, red_yy);
+          }
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < YS; ++j)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) xq[j][q] = xc[j][q];
+    }
+  };
+
+  for (int i = 0; i < nplanes; i += 3) {
+    body(i, accA, accB, accC);
+    if (i + 1 < nplanes) body(i + 1, accB, accC, accA);
+    if (i + 2 < nplanes) body(i + 2, accC, accA, accB);
+  }
+
+  if (!CHEBY && a.do_reduce) {
+    double v[2] = {red_xy, red_yy};
+    block_reduce_finalize<2>(v, red, red_out);
+  }
+}
+
+// ---- host side: tensor maps, tile geometry, launch ---------------------------------------------------
+typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmEncodeTiled tm_encode_fn() {
+  static PFN_tmEncodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_tmEncodeTiled)p;
+  });
+  return fn;
+}
+
+struct TmKey {
+  const void* base;
+  int nn0, nn1, nz, nc, bx, by;
+  long long px, plane, cs;
+  bool operator<(const TmKey& o) const {
+    if (base != o.base) return base < o.base;
+    if (nn0 != o.nn0) return nn0 < o.nn0;
+    if (nn1 != o.nn1) return nn1 < o.nn1;
+    if (nz != o.nz) return nz < o.nz;
+    if (nc != o.nc) return nc < o.nc;
+    if (bx != o.bx) return bx < o.bx;
+    if (by != o.by) return by < o.by;
+    if (px != o.px) return px < o.px;
+    if (plane != o.plane) return plane < o.plane;
+    return cs < o.cs;
+  }
+};
+
+// Tensor map of a padded field: (x, y, z incl. both ghost planes, component); out-of-range x/y -> 0.
+static int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by, CUtensorMap* out) {
+  static std::map<TmKey, CUtensorMap> cache;
+  static std::mutex mu;
+  TmKey k{(const void*)field, g.nn[0], g.nn[1], g.nzl + 2, nc, bx, by, g.PX, g.plane, g.comp_stride};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(k);
+  if (it != cache.end()) { *out = it->second; return 0; }
+  PFN_tmEncodeTiled enc = tm_encode_fn();
+  if (!enc) PDE_FAIL("cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t dims[4] = {(cuuint64_t)g.nn[0], (cuuint64_t)g.nn[1], (cuuint64_t)(g.nzl + 2), (cuuint64_t)nc};
+  cuuint64_t strides[3] = {(cuuint64_t)g.PX * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.comp_stride * 8};
+  cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1u, (cuuint32_t)nc};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  void* base = (void*)(field - g.plane);  // ghost plane below local plane 0
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) PDE_FAIL("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  if (cache.size() > 8192) cache.clear();
+  cache[k] = *out;
+  return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+struct SweepTune {
+  int nt, zc, ys, txmax;
+};
+static const SweepTune& sweep_tune() {
+  static SweepTune t = {env_int("PDE_B200_SW_NT", 384), env_int("PDE_B200_SW_ZC", 32), env_int("PDE_B200_SW_YS", 0),
+                        env_int("PDE_B200_SW_TXMAX", 192)};
+  return t;
+}
+
+template <int NC, int YS, bool CHEBY, bool HAS_B>
+static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
+  const SweepTune& tu = sweep_tune();
+  SweepGeom sw;
+  int txmax = tu.txmax < 32 ? 32 : (tu.txmax > 254 ? 254 : tu.txmax);
+  if (txmax > (NC == 1 ? 384 : 256) - 2) txmax = (NC == 1 ? 384 : 256) - 2;
+  sw.ntx = (g.nn[0] + txmax - 1) / txmax;
+  sw.tx = (g.nn[0] + sw.ntx - 1) / sw.ntx;
+  sw.tx += sw.tx & 1;  // even: the TMA box row must be a multiple of 16 bytes
+  sw.ntx = (g.nn[0] + sw.tx - 1) / sw.tx;
+  const int maxnt = NC == 1 ? 384 : 256;
+  int nt_target = tu.nt < 64 ? 64 : (tu.nt > maxnt ? maxnt : tu.nt);
+  sw.ns = nt_target / sw.tx;
+  if (sw.ns < 1) sw.ns = 1;
+  const int max_ns = (g.nn[1] + YS - 1) / YS;
+  if (sw.ns > max_ns) sw.ns = max_ns;
+  int nt = ((sw.tx * sw.ns + 31) / 32) * 32;
+  if (nt > maxnt) PDE_FAIL("sweep tile exceeds the thread limit");
+  sw.ty = sw.ns * YS;
+  sw.nty = (g.nn[1] + sw.ty - 1) / sw.ty;
+  sw.bx = sw.tx + 4;
+  sw.by = sw.ty + 2;
+  if (sw.bx > 256 || sw.by > 256) PDE_FAIL("sweep TMA box exceeds 256");
+  int zc = tu.zc < 2 ? 2 : tu.zc;
+  sw.nzc = (g.nzl + zc - 1) / zc;
+  sw.zc = (g.nzl + sw.nzc - 1) / sw.nzc;
+  sw.nzc = (g.nzl + sw.zc - 1) / sw.zc;
+  sw.stage_elems = ((sw.bx * sw.by * NC + 15) / 16) * 16;
+  const long long items = (long long)sw.ntx * sw.nty * sw.nzc;
+  if (items > RED_MAX_BLOCKS) PDE_FAIL("sweep grid exceeds the reduction buffer");
+  const size_t smem = (size_t)SW_STAGES * sw.stage_elems * sizeof(double) + SW_STAGES * sizeof(uint64_t);
+  auto kern = k_sweep3d<NC, YS, CHEBY, HAS_B>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  CUtensorMap tm;
+  PDE_OK(field_tensor_map(a.x, g, NC, sw.bx, sw.by, &tm));
+  Coef<NC> C;
+  for (int k = 0; k < PDE_NOFF; ++k)
+    for (int q = 0; q < NC * NC; ++q) C.c[k][q] = op.h_int[k * NC * NC + q];
+  SweepArgs sa;
+  sa.x = a.x; sa.b = a.b; sa.y = a.y; sa.d = a.d;
+  for (int i = 0; i < 3; ++i) sa.bconst[i] = a.bconst[i];
+  sa.bscale = a.bscale; sa.ascale = a.ascale; sa.c1 = a.c1; sa.c2 = a.c2;
+  sa.load_int = op.h_load_int;
+  for (int i = 0; i < 3; ++i) sa.dinv_int[i] = i < NC ? op.h_dinv_int[i] : 0.0;
+  sa.do_reduce = a.reduce_slot_xy >= 0;
+  double* out = sa.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
+  kern<<<(unsigned)items, nt, smem, c->stream>>>(tm, g, bc, C, op.coef, op.dinv, op.load, sa, sw, c->red, out);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a,
                         bool* handled) {
-  (void)c; (void)g; (void)bc; (void)op; (void)a;
+  *handled = false;
+  if (g.dim != 3 || g.nk != PDE_NOFF) return 0;
+  if (env_int("PDE_B200_NO_SWEEP", 0)) return 0;
+  // small grids (coarse multigrid levels) stay on the generic kernel: they are launch-latency bound
+  if (g.nn[0] < 32 || g.nn[1] < 8 || g.nzl < 4) return 0;
+  if ((long long)g.nn[0] * g.nn[1] * g.nzl < 4096) return 0;
+  const int ys = sweep_tune().ys;
+  *handled = true;
+#define SWEEP_DISPATCH(NC_, YS_)                                                                          \
+  do {                                                                                                   \
+    if (a.cheby) return a.b ? launch_sweep_t<NC_, YS_, true, true>(c, g, bc, op, a)                       \
+                            : launch_sweep_t<NC_, YS_, true, false>(c, g, bc, op, a);                     \
+    return a.b ? launch_sweep_t<NC_, YS_, false, true>(c, g, bc, op, a)                                   \
+               : launch_sweep_t<NC_, YS_, false, false>(c, g, bc, op, a);                                 \
+  } while (0)
+  if (op.ncomp == 1) {
+    if (ys == 2) SWEEP_DISPATCH(1, 2);
+    SWEEP_DISPATCH(1, 4);
+  }
+  if (op.ncomp == 3) {
+    if (ys == 1) SWEEP_DISPATCH(3, 1);
+    SWEEP_DISPATCH(3, 2);
+  }
   *handled = false;
   return 0;
 }

@@ -74,7 +74,11 @@ def _oracle_matrix(kind, dim, n, L, alpha, beta, lam, mu):
                                         ("heat", 3, [40, 12, 10]), ("mass", 3, [5, 5, 5]),
                                         ("stiffness", 2, [8, 8]), ("elasticity", 2, [9, 7]),
                                         ("elasticity", 3, [6, 5, 4]), ("elasticity", 3, [36, 6, 5]),
-                                        ("heat", 3, [1, 1, 1]), ("elasticity", 3, [2, 1, 3])])
+                                        ("heat", 3, [1, 1, 1]), ("elasticity", 3, [2, 1, 3]),
+                                        # sizes that take the TMA plane-sweep kernel (several x/y tiles, z chunks)
+                                        ("heat", 3, [70, 33, 40]), ("mass", 3, [64, 20, 9]),
+                                        ("heat", 3, [400, 10, 8]), ("elasticity", 3, [66, 20, 12]),
+                                        ("elasticity", 3, [200, 9, 36])])
 def test_operator_apply_matches_oracle(P, ctx, kind, dim, n, variant):
     L = [1.0, 0.6, 0.35][:dim]
     alpha, beta = (1.0, 0.013) if kind == "heat" else ((1.0, 0.0) if kind == "mass" else (0.0, 1.0))
