@@ -18,6 +18,7 @@
 
 #include <map>
 #include <mutex>
+#include <type_traits>
 
 #include "device.cuh"
 
@@ -126,10 +127,15 @@ __device__ __forceinline__ void plane_contrib(const Coef<NC>& C, const double (&
 // Row of a node whose element patch is incomplete (natural / traction-free faces): recomputed from the
 // 27-class table with global loads.  Rare (domain faces only), kept out of line to protect registers.
 template <int NC>
-__device__ __noinline__ void slow_row(const Grid& g, const double* __restrict__ coef, const double* __restrict__ x,
-                                      long long idx, int cls, double* acc) {
+struct RowVal {
+  double v[NC];
+};
+template <int NC>
+__device__ __noinline__ RowVal<NC> slow_row(const Grid& g, const double* __restrict__ coef, const double* __restrict__ x,
+                                            long long idx, int cls) {
+  RowVal<NC> r;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+  for (int c = 0; c < NC; ++c) r.v[c] = 0.0;
   for (int k = 0; k < PDE_NOFF; ++k) {
     const double* cf = coef + ((size_t)cls * PDE_NOFF + k) * (NC * NC);
     const long long off = g.koff[k];
@@ -139,8 +145,9 @@ __device__ __noinline__ void slow_row(const Grid& g, const double* __restrict__ 
 #pragma unroll
     for (int c = 0; c < NC; ++c)
 #pragma unroll
-      for (int q = 0; q < NC; ++q) acc[c] = fma(__ldg(cf + c * NC + q), xv[q], acc[c]);
+      for (int q = 0; q < NC; ++q) r.v[c] = fma(__ldg(cf + c * NC + q), xv[q], r.v[c]);
   }
+  return r;
 }
 
 template <int NC, int YS, bool CHEBY, bool HAS_B>
@@ -183,17 +190,22 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
   }
 
   const int lx = t % sw.tx;
-  const int st = t / sw.tx;
+  int st = t / sw.tx;
   const bool active = st < sw.ns;
+  if (!active) st = 0;  // surplus threads of the last warp shadow strip 0 and never store
   const int ix = x0 + lx;
   const int iy0 = y0 + st * YS;
   const int comp_elems = sw.bx * sw.by;
   // smem offset of V[0][0]: box row st*YS (= y -1), box column lx+1 (= x -1)
   const double* sbase = stage0 + (st * YS) * sw.bx + lx + 1;
 
-  // per-thread masks, constant over the z march: bit j describes node (ix, iy0+j)
-  unsigned valid = 0, dirxy = 0, slowxy = 0;
+  // per-thread node flags, constant over the z march: bit j describes node (ix, iy0+j).
+  //   mrow[j] = 0 for Dirichlet / out-of-range nodes, 1 for free nodes: masked rows need no branch.
+  unsigned valid = 0, slowxy = 0;
+  double mrow[YS];
   bool z_excl = false;  // "other_faces" predicate: side faces skip the x-end columns
+#pragma unroll
+  for (int j = 0; j < YS; ++j) mrow[j] = 0.0;
   if (active && ix < g.nn[0]) {
     const bool xe0 = ix == 0, xe1 = ix == g.nn[0] - 1;
     z_excl = bc.side_excl && (xe0 || xe1);
@@ -205,43 +217,47 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
       const bool ye0 = iy == 0, ye1 = iy == g.nn[1] - 1;
       bool d = (xe0 && bc.on[0]) || (xe1 && bc.on[1]);
       if (!d && !z_excl) d = (ye0 && bc.on[2]) || (ye1 && bc.on[3]);
-      if (d) dirxy |= 1u << j;
-      if (xe0 || xe1 || ye0 || ye1) slowxy |= 1u << j;
+      mrow[j] = d ? 0.0 : 1.0;
+      if (!d && (xe0 || xe1 || ye0 || ye1)) slowxy |= 1u << j;
     }
   }
   const long long col0 = (long long)g.PX * iy0 + ix;  // flat offset of (ix, iy0) inside a plane
+  const unsigned col0u = (unsigned)col0;
 
   double accA[YS][NC], accB[YS][NC], accC[YS][NC];
-  double xq[YS][NC];  // own-column values of the plane read one step earlier (the one that retires next)
+  // own-column values of the resident plane; the plane read one step earlier is the one that retires
+  double xA[YS][NC], xB[YS][NC], xC[YS][NC];
 #pragma unroll
   for (int j = 0; j < YS; ++j)
 #pragma unroll
-    for (int i = 0; i < NC; ++i) accA[j][i] = accB[j][i] = accC[j][i] = xq[j][i] = 0.0;
+    for (int i = 0; i < NC; ++i) accA[j][i] = accB[j][i] = accC[j][i] = xA[j][i] = xB[j][i] = xC[j][i] = 0.0;
   double red_xy = 0.0, red_yy = 0.0;
 
-  // One pipeline step: plane q = za-1+i is resident in stage i%STAGES; output plane q-1 retires.
-  auto body = [&](int i, double (&aP)[YS][NC], double (&a0)[YS][NC], double (&aM)[YS][NC]) {
+  // One pipeline step: plane q = za-1+i is resident in stage i%STAGES; output plane q-1 retires (FIN).
+  auto body = [&](auto fin_tag, int i, double (&aP)[YS][NC], double (&a0)[YS][NC], double (&aM)[YS][NC],
+                  double (&xprev)[YS][NC], double (&xcur)[YS][NC]) {
+    constexpr bool FIN = decltype(fin_tag)::value;
     const int stage = i % SW_STAGES;
     const uint32_t parity = (uint32_t)((i / SW_STAGES) & 1);
     const int zout = za + i - 2;
-    const bool fin = (i >= 2) && valid;
-    const long long obase = (long long)g.plane * zout + col0;
     // early global loads for the retiring outputs (consumed after the stencil arithmetic)
     double bv[YS][NC], dv[YS][NC];
-    if (fin && (HAS_B || CHEBY)) {
+    if (FIN && (HAS_B || CHEBY)) {
 #pragma unroll
-      for (int j = 0; j < YS; ++j)
+      for (int c = 0; c < NC; ++c) {
+        const double* __restrict__ bp = HAS_B ? a.b + (long long)g.plane * zout + c * g.comp_stride : nullptr;
+        const double* __restrict__ dp = CHEBY ? a.d + (long long)g.plane * zout + c * g.comp_stride : nullptr;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const long long ii = obase + (long long)g.PX * j + c * g.comp_stride;
+        for (int j = 0; j < YS; ++j) {
           const bool ok = (valid >> j) & 1u;
-          if (HAS_B) bv[j][c] = ok ? a.b[ii] : 0.0;
-          if (CHEBY) dv[j][c] = ok ? a.d[ii] : 0.0;
+          const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
+          if (HAS_B) bv[j][c] = ok ? bp[off] : 0.0;
+          if (CHEBY) dv[j][c] = ok ? dp[off] : 0.0;
         }
+      }
     }
     mbar_wait(bar0 + 8 * stage, parity);
-    double xc[YS][NC];
-    if (active) {
+    {
       double V[YS + 2][3][NC];
       const double* sp = sbase + (size_t)stage * sw.stage_elems;
 #pragma unroll
@@ -259,7 +275,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
 #pragma unroll
       for (int j = 0; j < YS; ++j)
 #pragma unroll
-        for (int q = 0; q < NC; ++q) xc[j][q] = V[j + 1][1][q];
+        for (int q = 0; q < NC; ++q) xcur[j][q] = V[j + 1][1][q];
       plane_contrib<NC, YS>(C, V, aP, a0, aM);
     }
     __syncthreads();  // every thread has consumed this stage
@@ -267,65 +283,78 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
       mbar_expect_tx(bar0 + 8 * stage, stage_bytes);
       tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i + SW_STAGES, 0, bar0 + 8 * stage);
     }
-    if (fin) {
+    if (FIN) {
       const int gz = zout + g.z0;
       const bool ze0 = g.nc[2] > 0 && gz == 0, ze1 = g.nc[2] > 0 && gz == g.nzg - 1;
-      const bool zslow = ze0 || ze1;
       const bool zdir = !z_excl && ((ze0 && bc.on[4]) || (ze1 && bc.on[5]));
+      const double mz = zdir ? 0.0 : 1.0;
+      unsigned todo = valid;
+      const unsigned slow = zdir ? 0u : ((ze0 || ze1) ? valid : slowxy);
+      // plane base pointers are uniform over the CTA; per-thread offsets fit 32 bits
+      const long long pbase = (long long)g.plane * zout;
+      if (slow) {  // incomplete element patches (domain faces only): class-table rows, emitted here
 #pragma unroll
-      for (int j = 0; j < YS; ++j) {
-        if (!((valid >> j) & 1u)) continue;
-        const long long idx = obase + (long long)g.PX * j;
-        if (((dirxy >> j) & 1u) || zdir) {  // Dirichlet row: masked
+        for (int j = 0; j < YS; ++j) {
+          if (!((slow >> j) & 1u) || mrow[j] == 0.0) continue;
+          todo &= ~(1u << j);
+          const int cls = node_class(g, ix, iy0 + j, gz);
+          const long long idx = pbase + col0 + (long long)g.PX * j;
+          const RowVal<NC> rv = slow_row<NC>(g, coef, a.x, idx, cls);
+          const double ld = __ldg(load + cls);
 #pragma unroll
           for (int c = 0; c < NC; ++c) {
             const long long ii = idx + c * g.comp_stride;
-            if (CHEBY) { a.d[ii] = 0.0; a.y[ii] = xq[j][c]; }
-            else if (a.y) a.y[ii] = 0.0;
+            const double B = HAS_B ? bv[j][c] : a.bconst[c] * ld;
+            if (CHEBY) {
+              const double dn = a.c1 * dv[j][c] + a.c2 * __ldg(dinv + cls * NC + c) * (B - rv.v[c]);
+              a.d[ii] = dn;
+              a.y[ii] = xprev[j][c] + dn;
+            } else {
+              const double yv = a.bscale * B + a.ascale * rv.v[c];
+              if (a.y) a.y[ii] = yv;
+              red_xy = fma(xprev[j][c], yv, red_xy);
+              red_yy = fma(yv, yv, red_yy);
+            }
           }
-          continue;
         }
-        double acc[NC], di[NC], ld;
+      }
+      // interior-class rows: Dirichlet / out-of-range / already emitted rows are masked by m = 0
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { acc[c] = aP[j][c]; di[c] = a.dinv_int[c]; }
-        ld = a.load_int;
-        if (((slowxy >> j) & 1u) || zslow) {  // incomplete element patch: class-table row (domain faces only)
-          const int iy = iy0 + j;
-          const int cls = node_class(g, ix, iy, gz);
-          slow_row<NC>(g, coef, a.x, idx, cls, acc);
+      for (int c = 0; c < NC; ++c) {
+        const double* __restrict__ dcp = CHEBY ? a.d + pbase + c * g.comp_stride : nullptr;
+        double* __restrict__ dp = const_cast<double*>(dcp);
+        double* __restrict__ yp = a.y ? a.y + pbase + c * g.comp_stride : nullptr;
+        const double bB = a.bscale * a.bconst[c] * a.load_int;  // constant load term of the interior class
+        const double c2d = a.c2 * a.dinv_int[c];
 #pragma unroll
-          for (int c = 0; c < NC; ++c) di[c] = __ldg(dinv + cls * NC + c);
-          ld = __ldg(load + cls);
-        }
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const long long ii = idx + c * g.comp_stride;
-          const double B = HAS_B ? bv[j][c] : a.bconst[c] * ld;
+        for (int j = 0; j < YS; ++j) {
+          const bool on = (todo >> j) & 1u;
+          const double m = on ? mrow[j] * mz : 0.0;
+          const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
           if (CHEBY) {
-            const double dn = a.c1 * dv[j][c] + a.c2 * di[c] * (B - acc[c]);
-            a.d[ii] = dn;
-            a.y[ii] = xq[j][c] + dn;
+            const double B = HAS_B ? bv[j][c] : a.bconst[c] * a.load_int;
+            const double dn = m * fma(a.c1, dv[j][c], c2d * (B - aP[j][c]));
+            if (on) { dp[off] = dn; yp[off] = xprev[j][c] + dn; }
           } else {
-            const double yv = a.bscale * B + a.ascale * acc[c];
-            if (a.y) a.y[ii] = yv;
-            red_xy = fma(xq[j][c], yv, red_xy);
+            const double yv = m * (HAS_B ? fma(a.ascale, aP[j][c], a.bscale * bv[j][c]) : fma(a.ascale, aP[j][c], bB));
+            if (on && yp) yp[off] = yv;
+            red_xy = fma(xprev[j][c], yv, red_xy);
             red_yy = fma(yv, yv, red_yy);
           }
         }
       }
     }
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < YS; ++j)
-#pragma unroll
-        for (int q = 0; q < NC; ++q) xq[j][q] = xc[j][q];
-    }
   };
 
-  for (int i = 0; i < nplanes; i += 3) {
-    body(i, accA, accB, accC);
-    if (i + 1 < nplanes) body(i + 1, accB, accC, accA);
-    if (i + 2 < nplanes) body(i + 2, accC, accA, accB);
+  using T_ = std::true_type;
+  using F_ = std::false_type;
+  // steps 0 and 1 only fill the pipeline; output za retires at step 2
+  body(F_{}, 0, accA, accB, accC, xC, xA);
+  body(F_{}, 1, accB, accC, accA, xA, xB);
+  for (int i = 2; i < nplanes; i += 3) {
+    body(T_{}, i, accC, accA, accB, xB, xC);
+    if (i + 1 < nplanes) body(T_{}, i + 1, accA, accB, accC, xC, xA);
+    if (i + 2 < nplanes) body(T_{}, i + 2, accB, accC, accA, xA, xB);
   }
 
   if (!CHEBY && a.do_reduce) {
@@ -402,7 +431,7 @@ struct SweepTune {
   int nt, zc, ys, txmax;
 };
 static const SweepTune& sweep_tune() {
-  static SweepTune t = {env_int("PDE_B200_SW_NT", 384), env_int("PDE_B200_SW_ZC", 32), env_int("PDE_B200_SW_YS", 0),
+  static SweepTune t = {env_int("PDE_B200_SW_NT", 192), env_int("PDE_B200_SW_ZC", 64), env_int("PDE_B200_SW_YS", 0),
                         env_int("PDE_B200_SW_TXMAX", 192)};
   return t;
 }
