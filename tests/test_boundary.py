@@ -1,0 +1,157 @@
+"""Drop-in boundary: tool names / keyword arguments / defaults equal the reference's (golden JSON made by
+scripts/make_golden_signatures.py from /root/reference/fenics_mcp_server.py), the C-ABI library
+exports every symbol include/pde_b200.h declares, and (GPU) the tools work through MCP."""
+import asyncio
+import inspect
+import json
+import os
+import pickle
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_signatures.json")))
+IN_SCOPE = ["solve_heat_1D", "solve_heat_2D", "solve_heat_3D", "solve_elasticity_1D_static",
+            "solve_elasticity_2D_static", "solve_elasticity_3D_static"]
+
+
+@pytest.fixture(scope="module")
+def server():
+    import fenics_mcp_server as s
+    return s
+
+
+def test_server_and_tool_names(server):
+    assert server.mcp.name == GOLD["server_name"] == "FEniCS-Heat"
+    tools = asyncio.run(server.mcp.list_tools())
+    assert sorted(t.name for t in tools) == sorted(GOLD["tools"])
+
+
+@pytest.mark.parametrize("name", sorted(GOLD["tools"]))
+def test_tool_signature_matches_reference(server, name):
+    fn = getattr(server, name)
+    ours = inspect.signature(fn)
+    ref = GOLD["tools"][name]["args"]
+    assert [p for p in ours.parameters] == [a["name"] for a in ref]
+    for a in ref:
+        p = ours.parameters[a["name"]]
+        if a["has_default"]:
+            assert p.default == a["default"], (name, a["name"])
+        else:
+            assert p.default is inspect.Parameter.empty
+    assert ours.return_annotation.__name__ == GOLD["tools"][name]["returns"]
+
+
+@pytest.mark.parametrize("name", ["_solve_heat_1d_raw", "_solve_heat_2d_raw", "_solve_heat_3d_raw",
+                                  "_solve_elasticity_1d_static", "_solve_elasticity_2d_static",
+                                  "_solve_elasticity_3d_static"])
+def test_raw_solver_signature_is_a_superset(name):
+    import pde_solver_b200 as P
+    ours = inspect.signature(getattr(P, name))
+    ref = GOLD["raw"][name]["args"]
+    positional = [p.name for p in ours.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD]
+    assert positional == [a["name"] for a in ref]          # same names, same order
+    for a in ref:
+        if a["has_default"]:
+            assert ours.parameters[a["name"]].default == a["default"]
+    extra = [p for p in ours.parameters.values() if p.kind == p.KEYWORD_ONLY]
+    assert all(p.default is not inspect.Parameter.empty for p in extra)   # additions are optional
+
+
+def test_result_dataclasses_have_reference_fields():
+    from pde_solver_b200.fields import PlotResult, SolveResult, TimeSeriesField
+    assert list(TimeSeriesField.__dataclass_fields__) == ["coords", "values", "times", "dim", "meta"]
+    assert list(SolveResult.__dataclass_fields__) == ["data_file", "dim", "meta"]
+    assert list(PlotResult.__dataclass_fields__) == ["html_path"]
+
+
+def test_cabi_exports_every_declared_symbol():
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "pde_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(pde_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    from pde_solver_b200 import _lib
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_out_of_scope_tools_raise_clearly(server):
+    with pytest.raises(NotImplementedError, match="outside"):
+        server.solve_heat_1D_cylindrical()
+    with pytest.raises(NotImplementedError):
+        server.solve_heat_3D_spherical()
+
+
+def test_plot_tool_accepts_solver_pickles(server, tmp_path):
+    from pde_solver_b200.fields import TimeSeriesField
+    f = TimeSeriesField(coords=[[0, 0, 0], [1, 0, 0], [2, 0, 0]], values=[[0, 1, 2], [1, 2, 3]], times=[0.0, 0.1],
+                        dim=1, meta={"name": "temperature", "unit": "°C"})
+    p = tmp_path / "heat_1d_deadbeef.pkl"
+    pickle.dump(f, open(p, "wb"))
+    r = server.plot_time_series_field_from_file(str(p), output_dir=str(tmp_path / "plots"))
+    assert os.path.exists(r.html_path) and r.html_path.endswith("heat_1d_deadbeef.html")
+    with pytest.raises(ValueError):
+        server.plot_time_series_field([[0, 0, 0]], [[1, 2]], [0.0], output_dir=str(tmp_path))
+
+
+def test_product_path_does_not_import_the_oracle():
+    # the oracle is test infrastructure: nothing under the package or the server may reference it
+    for base in (os.path.join(ROOT, "pde-solver_b200"), ROOT):
+        for fn in os.listdir(base):
+            if fn.endswith(".py") and fn not in ("bench.py", "__graft_entry__.py"):
+                src = open(os.path.join(base, fn)).read()
+                assert "oracle" not in src.replace("# oracle", ""), fn
+
+
+# ------------------------------------------------------------------ GPU: through MCP
+@pytest.mark.gpu
+def test_call_tool_in_process(server, tmp_path):
+    from oracle import fem_oracle as fo
+    args = dict(Lx=1.0, Ly=1.0, Lz=1.0, nx=8, ny=8, nz=8, diffusivity=1.0, T_boundary=0.0, T_initial=20.0, dt=0.01,
+                num_steps=4, data_dir=str(tmp_path))
+    res = asyncio.run(server.mcp.call_tool("solve_heat_3D", args))
+    payload = res[1] if isinstance(res, tuple) else json.loads(res[0].text)
+    assert set(payload) == {"data_file", "dim", "meta"} and payload["dim"] == 3
+    assert re.fullmatch(r"heat_3d_[0-9a-f]{8}\.pkl", os.path.basename(payload["data_file"]))
+    field = pickle.load(open(payload["data_file"], "rb"))
+    ref = fo.solve_heat(3, [1, 1, 1], [8, 8, 8], 1.0, T_initial=20.0, dt=0.01, num_steps=4)
+    assert np.asarray(field.values).shape == (5, 729) and len(field.times) == 5
+    assert isinstance(field.values, list) and isinstance(field.coords[0], list)      # reference layout
+    assert fo.rel_l2(np.asarray(field.values)[-1], ref.values[-1]) <= 1e-8
+    plot = server.plot_time_series_field_from_file(payload["data_file"], output_dir=str(tmp_path / "plots"))
+    assert os.path.exists(plot.html_path)
+    res = asyncio.run(server.mcp.call_tool("solve_elasticity_3D_static", dict(
+        Lx=1.0, Ly=0.2, Lz=0.2, nx=10, ny=2, nz=2, body_fz=-76518.0, quantity="strain", data_dir=str(tmp_path))))
+    payload = res[1] if isinstance(res, tuple) else json.loads(res[0].text)
+    assert re.fullmatch(r"elasticity_3d_strain_[0-9a-f]{8}\.pkl", os.path.basename(payload["data_file"]))
+    assert payload["meta"]["name"] == "von_mises_strain"
+
+
+@pytest.mark.gpu
+def test_stdio_round_trip(tmp_path):
+    """Launch the server the way the orchestrator does (python fenics_mcp_server.py over stdio)."""
+    from mcp import ClientSession, StdioServerParameters
+    from mcp.client.stdio import stdio_client
+
+    async def go():
+        params = StdioServerParameters(command=sys.executable, args=[os.path.join(ROOT, "fenics_mcp_server.py")],
+                                       cwd=str(tmp_path))
+        async with stdio_client(params) as (r, w):
+            async with ClientSession(r, w) as s:
+                await s.initialize()
+                names = sorted(t.name for t in (await s.list_tools()).tools)
+                out = await s.call_tool("solve_heat_1D", dict(length=2.0, nx=100, T_left=20.0, T_right=0.0,
+                                                              T_initial=0.0, dt=0.01, num_steps=10))
+                return names, out
+    names, out = asyncio.run(go())
+    assert names == sorted(GOLD["tools"])
+    assert not out.isError
+    payload = json.loads(out.content[0].text)
+    path = payload["data_file"] if os.path.isabs(payload["data_file"]) else os.path.join(str(tmp_path), payload["data_file"])
+    field = pickle.load(open(path, "rb"))
+    assert len(field.values) == 11 and len(field.values[0]) == 101 and field.meta["pde"] == "heat"
