@@ -230,7 +230,7 @@ extern "C" int pde_heat_open(pde_ctx* c, const pde_heat_params* p, const pde_sol
     s->nloc = (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzl;
     if ((rc = s->dense.alloc(sizeof(double) * s->nloc))) break;
     long long ndofs = (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzg;
-    if (s->o.precond != PDE_PRECOND_JACOBI && c->world == 1) {
+    if (s->o.precond != PDE_PRECOND_JACOBI) {
       if ((rc = s->mg.build(c, s->A, PDE_OP_HEAT, alpha, beta))) break;
       s->mg.nu = s->o.cheby_degree > 0 ? s->o.cheby_degree : 2;
       s->mg.ratio = s->o.cheby_ratio > 1 ? s->o.cheby_ratio : 8.0;
@@ -470,7 +470,7 @@ static int solve_with(pde_ctx* c, OpGuard& G, const pde_op_params* p, const pde_
   const int nc = G.A.tab.ncomp;
   long long ndofs = (long long)G.A.g.nn[0] * G.A.g.nn[1] * G.A.g.nzg * nc;
   bool use_mg = false;
-  if (o.precond != PDE_PRECOND_JACOBI && c->world == 1) {
+  if (o.precond != PDE_PRECOND_JACOBI) {
     double p0 = p->kind == PDE_OP_ELASTICITY ? p->lam : (p->kind == PDE_OP_MASS ? 1.0 : (p->kind == PDE_OP_STIFFNESS ? 0.0 : p->alpha));
     double p1 = p->kind == PDE_OP_ELASTICITY ? p->mu : (p->kind == PDE_OP_MASS ? 0.0 : (p->kind == PDE_OP_STIFFNESS ? 1.0 : p->beta));
     PDE_OK(G.mg.build(c, G.A, p->kind == PDE_OP_ELASTICITY ? PDE_OP_ELASTICITY : PDE_OP_HEAT, p0, p1));
@@ -538,7 +538,6 @@ extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const
                                     double* field_out, double* disp_out, pde_stats* st_out, pde_stats* st_proj_out) {
   if (!c || !p || !field_out) PDE_FAIL("null argument");
   CUDA_OK(cudaSetDevice(c->device));
-  if (c->world > 1) PDE_FAIL("pde_elasticity_solve: multi-GPU slabs are not wired for this entry point yet");
   pde_solver_opts o;
   if (o_in) o = *o_in; else pde_solver_opts_default(&o);
   if (!(p->E > 0)) PDE_FAIL("E must be > 0");
@@ -577,6 +576,7 @@ extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const
   a.x = G.x.p; a.y = G.r.p; a.bscale = 1.0; a.ascale = -1.0; a.reduce_slot_xy = S_XY;
   for (int i = 0; i < nc; ++i) a.bconst[i] = p->body[i];
   PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
   double bn2;
   PDE_OK(read_scal(c, S_YY, 1, &bn2));
   PDE_OK(solve_with(c, G, &op, o, G.x.p, G.r.p, bn2, &st));
@@ -602,8 +602,10 @@ extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
   const long long l1 = c->launches;
   const int mode = dim == 1 ? (p->quantity == 1 ? 2 : 3) : (p->quantity == 1 ? 1 : 0);
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, G.x.p));
   PDE_OK(launch_cell_rhs(c, g, nc, sg, G.x.p, P.r.p, mode, lam, mu, p->E));
   PDE_OK(launch_dot(c, g, 1, P.r.p, P.r.p, S_TMP0));
+  if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_TMP0, 1));
   double pn2;
   PDE_OK(read_scal(c, S_TMP0, 1, &pn2));
   pde_solver_opts po = o;

@@ -95,6 +95,12 @@ int comm_allreduce_scal(pde_ctx* c, int slot, int count) {
   return 0;
 }
 
+int comm_allreduce_buf(pde_ctx* c, double* buf, size_t count) {
+  if (c->world == 1 || count == 0) return 0;
+  NCCL_OK(c->nccl->AllReduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream));
+  return 0;
+}
+
 int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* f) {
   if (c->world == 1) return 0;
   const size_t n = (size_t)g.plane;

@@ -199,6 +199,9 @@ int launch_unpack(pde_ctx* c, const Grid& g, int ncomp, const double* dense, dou
 int launch_cell_rhs(pde_ctx* c, const Grid& g, int ncomp, const SimplexGeom& sg, const double* u, double* rhs,
                     int mode, double lam, double mu, double Emod);
 int launch_dense_solve(pde_ctx* c, int n, const double* Ainv, const long long* idx, const double* b, double* x);
+// multi-rank coarse solve: idx[j] < 0 marks dofs owned by another rank
+int launch_dense_gather(pde_ctx* c, int n, const long long* idx, const double* b, double* bglob);
+int launch_dense_solve_owned(pde_ctx* c, int n, const double* Ainv, const long long* idx, const double* bglob, double* x);
 // mesh
 int launch_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* out);
 int launch_mesh_cells(pde_ctx* c, int dim, const int32_t n[3], int sorted, int ncomp, int layout, int32_t* out);
@@ -207,3 +210,4 @@ int launch_bc_mask(pde_ctx* c, const Grid& g, const BcDev& bc, uint8_t* mask, do
 // comm.cu
 int comm_allreduce_scal(pde_ctx* c, int slot, int count);
 int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* field);
+int comm_allreduce_buf(pde_ctx* c, double* buf, size_t count);

@@ -455,6 +455,40 @@ int launch_dense_solve(pde_ctx* c, int n, const double* Ainv, const long long* i
   return 0;
 }
 
+// multi-rank coarsest level: every rank holds the global dense inverse; the right-hand side is assembled
+// by an all-reduce of the owned entries, each rank then computes the rows it owns
+__global__ void __launch_bounds__(256)
+k_dense_gather(int n, const long long* __restrict__ idx, const double* __restrict__ b, double* __restrict__ bglob) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) bglob[j] = idx[j] >= 0 ? b[idx[j]] : 0.0;
+}
+__global__ void __launch_bounds__(256)
+k_dense_solve_owned(int n, const double* __restrict__ Ainv, const long long* __restrict__ idx,
+                    const double* __restrict__ bglob, double* __restrict__ x) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n || idx[warp] < 0) return;
+  double s = 0.0;
+  for (int j = lane; j < n; j += 32) s = fma(Ainv[(size_t)warp * n + j], bglob[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) x[idx[warp]] = s;
+}
+int launch_dense_gather(pde_ctx* c, int n, const long long* idx, const double* b, double* bglob) {
+  if (n <= 0) return 0;
+  k_dense_gather<<<(n + 255) / 256, 256, 0, c->stream>>>(n, idx, b, bglob);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_dense_solve_owned(pde_ctx* c, int n, const double* Ainv, const long long* idx, const double* bglob,
+                             double* x) {
+  if (n <= 0) return 0;
+  k_dense_solve_owned<<<(n * 32 + 255) / 256, 256, 0, c->stream>>>(n, Ainv, idx, bglob, x);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // fields: initial condition / BC values / dense <-> padded layout
 // ----------------------------------------------------------------------------------------------

@@ -146,9 +146,13 @@ static int dense_inverse_spd(std::vector<double>& A, int n) {
   return 0;
 }
 
-static int build_dense_coarse(pde_ctx* c, MGLevel& L) {
-  const Grid& g = L.op.g;
+// Dense inverse of the coarsest operator.  It is built on the GLOBAL coarse grid (identical on every
+// rank); idx maps global free dof j to this rank's flat local index, or -1 if another rank owns it.
+static int build_dense_coarse(pde_ctx* c, MGLevel& L, int dim, const int32_t n_user[3], const double L_user[3]) {
+  const Grid& gl = L.op.g;
   const int nc = L.op.tab.ncomp, nn = nc * nc;
+  Grid g;  // global view
+  PDE_OK(make_grid(dim, n_user, L_user, 0, 1, &g));
   std::vector<long long> idx;
   std::vector<int> dofid;
   long long n = count_free_and_index(g, L.op.bc, nc, &idx, &dofid);
@@ -170,9 +174,19 @@ static int build_dense_coarse(pde_ctx* c, MGLevel& L) {
         }
       }
   if (dense_inverse_spd(A, (int)n)) PDE_FAIL("coarse operator is not positive definite");
+  // global flat index -> local flat index (or -1)
+  for (auto& v : idx) {
+    const int comp = (int)(v / g.comp_stride);
+    const long long r = v % g.comp_stride;
+    const int gz = (int)(r / g.plane);
+    const long long inplane = r % g.plane;
+    if (gz < gl.z0 || gz >= gl.z0 + gl.nzl) v = -1;
+    else v = inplane + gl.plane * (gz - gl.z0) + comp * gl.comp_stride;
+  }
   L.n_dense = (int)n;
   CUDA_OK(cudaMalloc(&L.Ainv, A.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&L.idx, idx.size() * sizeof(long long)));
+  CUDA_OK(cudaMalloc(&L.bglob, (size_t)n * sizeof(double)));
   CUDA_OK(cudaMemcpyAsync(L.Ainv, A.data(), A.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaMemcpyAsync(L.idx, idx.data(), idx.size() * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -204,16 +218,18 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
     if (level > 0) PDE_OK(L->b.alloc(c, g, ncomp));
     lv.push_back(std::move(L));
     // can we coarsen further?
-    bool can = c->world == 1;
+    bool can = true;
     if (const char* ml = getenv("PDE_B200_MAX_LEVELS")) can = can && (level + 1 < atoi(ml));
     int32_t nc2[3] = {0, 0, 0};
     for (int q = 0; q < nax; ++q) {
       if (n[q] % 2 != 0 || n[q] < 2) can = false;
       nc2[q] = n[q] / 2;
     }
+    // slabs: the coarse partition must nest in the fine one (rank r owns coarse planes z0/2 ...)
+    if (c->world > 1 && n[nax - 1] % (2 * c->world) != 0) can = false;
     if (can) {
       Grid gc;
-      PDE_OK(make_grid(dim, nc2, Lu, c->rank, c->world, &gc));
+      PDE_OK(make_grid(dim, nc2, Lu, 0, 1, &gc));  // global view: every rank takes the same decision
       long long nodes = (long long)gc.nn[0] * gc.nn[1] * gc.nzl;
       if (nodes <= 200000) {
         long long nfree = count_free_and_index(gc, fine.bc, ncomp, nullptr, nullptr);
@@ -225,10 +241,12 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
   }
   // coarsest level: dense inverse if small enough
   MGLevel& Lc = *lv.back();
-  long long nodes = (long long)Lc.op.g.nn[0] * Lc.op.g.nn[1] * Lc.op.g.nzl;
+  long long nodes = (long long)Lc.op.g.nn[0] * Lc.op.g.nn[1] * Lc.op.g.nzg;
   if (lv.size() > 1 && nodes * ncomp <= 4 * PDE_DENSE_MAX) {
-    long long nfree = count_free_and_index(Lc.op.g, Lc.op.bc, ncomp, nullptr, nullptr);
-    if (nfree > 0 && nfree <= PDE_DENSE_MAX) PDE_OK(build_dense_coarse(c, Lc));
+    Grid gg;
+    PDE_OK(make_grid(dim, n, Lu, 0, 1, &gg));
+    long long nfree = count_free_and_index(gg, Lc.op.bc, ncomp, nullptr, nullptr);
+    if (nfree > 0 && nfree <= PDE_DENSE_MAX) PDE_OK(build_dense_coarse(c, Lc, dim, n, Lu));
   }
   return 0;
 }
@@ -239,6 +257,7 @@ void Hierarchy::release() {
     L->b.release(); L->xa.release(); L->xb.release(); L->r.release(); L->d.release();
     if (L->Ainv) cudaFree(L->Ainv);
     if (L->idx) cudaFree(L->idx);
+    if (L->bglob) cudaFree(L->bglob);
   }
   lv.clear();
 }
@@ -304,7 +323,13 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
   {
     MGLevel& L = *lv[nl - 1];
     const double* b = nl == 1 ? b0 : L.b.p;
-    if (L.n_dense > 0) PDE_OK(launch_dense_solve(c, L.n_dense, L.Ainv, L.idx, b, cur[nl - 1]));
+    if (L.n_dense > 0 && c->world == 1) {
+      PDE_OK(launch_dense_solve(c, L.n_dense, L.Ainv, L.idx, b, cur[nl - 1]));
+    } else if (L.n_dense > 0) {
+      PDE_OK(launch_dense_gather(c, L.n_dense, L.idx, b, L.bglob));
+      PDE_OK(comm_allreduce_buf(c, L.bglob, (size_t)L.n_dense));
+      PDE_OK(launch_dense_solve_owned(c, L.n_dense, L.Ainv, L.idx, L.bglob, cur[nl - 1]));
+    }
     else PDE_OK(smooth(c, L, b, &cur[nl - 1], &oth[nl - 1], nl == 1 ? nu : coarse_sweeps, true, nl == 1 ? ratio : 30.0));
   }
   for (int l = nl - 2; l >= 0; --l) {

@@ -29,7 +29,8 @@ struct MGLevel {
   // coarsest level
   int n_dense = 0;
   double* Ainv = nullptr;
-  long long* idx = nullptr;
+  long long* idx = nullptr;   // flat local index of global free dof j (-1: owned by another rank)
+  double* bglob = nullptr;    // multi-rank: global coarse right-hand side (all-reduced)
 };
 
 struct Hierarchy {

@@ -206,7 +206,7 @@ int make_grid(int dim, const int32_t n[3], const double L[3], int rank, int worl
   g->plane = (long long)g->PX * g->PY;
   g->nzg = g->nn[2];
   if (world > 1) {
-    if (g->nc[2] < 2 * world) PDE_FAIL("slab partition needs at least 2 cell layers per GPU");
+    if (g->nc[2] < world) PDE_FAIL("slab partition needs at least 1 cell layer per GPU along the slowest axis");
     int base = g->nc[2] / world;
     g->z0 = rank * base;
     g->nzl = (rank == world - 1) ? (g->nzg - g->z0) : base;
