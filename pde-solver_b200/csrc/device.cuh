@@ -158,6 +158,7 @@ struct OpDev {
   double h_dinv_int[3] = {0, 0, 0};  // interior class Jacobi diagonal inverse
   double h_load_int = 0;             // interior class load (integral of the hat function)
   double gershgorin = 0;
+  int uniform_diag = 0;  // every free node has the interior-class diagonal (all faces Dirichlet)
 };
 
 struct StencilArgs {
@@ -168,7 +169,9 @@ struct StencilArgs {
   double bconst[3] = {0, 0, 0};
   double bscale = 0, ascale = 1;  // y = bscale*B + ascale*(A x)
   double c1 = 0, c2 = 0;          // cheby: d = c1*d + c2*dinv*(B - A x); y = x + d
-  int cheby = 0;
+  double s0 = 0;                  // cheby == 2: coefficient of the (implicit) first sweep, d1 = s0*dinv*b
+  int cheby = 0;                  // 1: one sweep; 2: first TWO sweeps from a zero guess, x = right-hand side
+                                  // reduce_slot_xy with cheby: receives sum B.y (one value)
   int reduce_slot_xy = -1;        // scal slot receiving sum x.y (and +1: sum y.y) ; -1: none
   int variant = 0;
 };

@@ -24,8 +24,9 @@ struct StencilDev {
   double* y;
   double* d;
   double bconst[3];
-  double bscale, ascale, c1, c2;
+  double bscale, ascale, c1, c2, s0;
   int do_reduce;
+  int first2;
 };
 
 template <int NC, bool CHEBY>
@@ -94,10 +95,21 @@ k_stencil(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
         const long long ii = idx + i * g.comp_stride;
         const double B = a.b ? a.b[ii] : a.bconst[i] * ld;
         if (CHEBY) {
-          const double r = B - acc[i];
-          const double dn = a.c1 * a.d[ii] + a.c2 * __ldg(dinv + cls * NC + i) * r;
+          const double di = __ldg(dinv + cls * NC + i);
+          double dn, yv, Bv;
+          if (a.first2) {  // x holds the right-hand side; x1 = d1 = s0 D^-1 b (uniform diagonal)
+            Bv = a.x[ii];
+            const double d1 = a.s0 * di * Bv;
+            dn = a.c1 * d1 + a.c2 * di * (Bv - a.s0 * di * acc[i]);
+            yv = d1 + dn;
+          } else {
+            Bv = B;
+            dn = a.c1 * a.d[ii] + a.c2 * di * (B - acc[i]);
+            yv = a.x[ii] + dn;
+          }
           a.d[ii] = dn;
-          a.y[ii] = a.x[ii] + dn;
+          a.y[ii] = yv;
+          if (a.do_reduce) acc_xy = fma(Bv, yv, acc_xy);
         } else {
           const double yv = a.bscale * B + a.ascale * acc[i];
           if (a.y) a.y[ii] = yv;
@@ -109,9 +121,14 @@ k_stencil(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
       }
     }
   }
-  if (!CHEBY && a.do_reduce) {
-    double v[2] = {acc_xy, acc_yy};
-    block_reduce_finalize<2>(v, red, red_out);
+  if (a.do_reduce) {
+    if (CHEBY) {
+      double v[1] = {acc_xy};
+      block_reduce_finalize<1>(v, red, red_out);
+    } else {
+      double v[2] = {acc_xy, acc_yy};
+      block_reduce_finalize<2>(v, red, red_out);
+    }
   }
 }
 
@@ -123,7 +140,8 @@ static int launch_stencil_t(pde_ctx* c, const Grid& g, const BcDev& bc, const Op
   StencilDev sd;
   sd.x = a.x; sd.b = a.b; sd.y = a.y; sd.d = a.d;
   for (int i = 0; i < 3; ++i) sd.bconst[i] = a.bconst[i];
-  sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2;
+  sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2; sd.s0 = a.s0;
+  sd.first2 = a.cheby == 2;
   sd.do_reduce = a.reduce_slot_xy >= 0;
   RowLaunch rl = row_launch(c, g);
   double* out = sd.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;

@@ -56,6 +56,13 @@ int Operator::upload(pde_ctx* c) {
     for (int q = 0; q < nn; ++q) dev.h_int[k * nn + q] = tab.coef[((size_t)13 * PDE_NOFF + k) * nn + q];
   for (int i = 0; i < nc; ++i) dev.h_dinv_int[i] = dinv[13 * nc + i];
   dev.h_load_int = tab.load[13];
+  {
+    // all faces of the present axes Dirichlet (and no other_faces exclusion): every free node is interior class
+    bool u = !bc.side_excl;
+    for (int ax = 0; ax < 3; ++ax)
+      if (g.nc[ax] > 0 && !(bc.on[2 * ax] && bc.on[2 * ax + 1])) u = false;
+    dev.uniform_diag = u ? 1 : 0;
+  }
   CUDA_OK(cudaMalloc(&dev.coef, tab.coef.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&dev.dinv, dinv.size() * sizeof(double)));
   CUDA_OK(cudaMalloc(&dev.load, PDE_NCLASS * sizeof(double)));
@@ -281,12 +288,28 @@ struct Cheby {
   }
 };
 
+// Chebyshev(Jacobi) smoothing.  dot_slot >= 0: the LAST sweep also leaves sum b.x_new in that scalar slot
+// (*dot_done tells whether a sweep could do it).
 static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double** oth, int sweeps, bool zero_guess,
-                  double ratio) {
+                  double ratio, int dot_slot = -1, bool* dot_done = nullptr) {
   Cheby ch;
   ch.init(L.op.dev.gershgorin, ratio);
   int k0 = 0;
-  if (zero_guess) {
+  if (dot_done) *dot_done = false;
+  if (zero_guess && sweeps >= 2 && L.op.dev.uniform_diag) {
+    // sweeps 0 and 1 in one pass over the data: x1 = s0 D^-1 b never touches memory
+    StencilArgs a;
+    double c1, s0;
+    ch.coef(0, &c1, &s0);
+    a.cheby = 2;
+    a.s0 = s0;
+    ch.coef(1, &a.c1, &a.c2);
+    a.x = b; a.y = *cur; a.d = L.d.p;
+    if (dot_slot >= 0 && sweeps == 2) { a.reduce_slot_xy = dot_slot; if (dot_done) *dot_done = true; }
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, const_cast<double*>(b)));
+    PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
+    k0 = 2;
+  } else if (zero_guess) {
     double c1, c2;
     ch.coef(0, &c1, &c2);
     PDE_OK(launch_cheby_first(c, L.op.g, L.op.bc, L.op.dev, b, L.d.p, *cur, c2));
@@ -297,6 +320,7 @@ static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double*
     a.cheby = 1;
     a.x = *cur; a.y = *oth; a.b = b; a.d = L.d.p;
     ch.coef(k, &a.c1, &a.c2);
+    if (dot_slot >= 0 && k == sweeps - 1) { a.reduce_slot_xy = dot_slot; if (dot_done) *dot_done = true; }
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, *cur));
     PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
     std::swap(*cur, *oth);
@@ -304,7 +328,9 @@ static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double*
   return 0;
 }
 
-int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double** z_out) {
+int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double** z_out, int dot_slot,
+                      bool* dot_done) {
+  if (dot_done) *dot_done = false;
   (void)fine;
   const int nl = (int)lv.size();
   std::vector<double*> cur(nl), oth(nl);
@@ -330,14 +356,15 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
       PDE_OK(comm_allreduce_buf(c, L.bglob, (size_t)L.n_dense));
       PDE_OK(launch_dense_solve_owned(c, L.n_dense, L.Ainv, L.idx, L.bglob, cur[nl - 1]));
     }
-    else PDE_OK(smooth(c, L, b, &cur[nl - 1], &oth[nl - 1], nl == 1 ? nu : coarse_sweeps, true, nl == 1 ? ratio : 30.0));
+    else PDE_OK(smooth(c, L, b, &cur[nl - 1], &oth[nl - 1], nl == 1 ? nu : coarse_sweeps, true, nl == 1 ? ratio : 30.0,
+                       nl == 1 ? dot_slot : -1, nl == 1 ? dot_done : nullptr));
   }
   for (int l = nl - 2; l >= 0; --l) {
     MGLevel& L = *lv[l];
     const double* b = l == 0 ? b0 : L.b.p;
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, lv[l + 1]->op.g, L.op.dev.ncomp, cur[l + 1]));
     PDE_OK(launch_prolong_add(c, L.op.g, lv[l + 1]->op.g, L.op.bc, L.op.dev.ncomp, cur[l + 1], cur[l]));
-    PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, false, ratio));
+    PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, false, ratio, l == 0 ? dot_slot : -1, l == 0 ? dot_done : nullptr));
   }
   *z_out = cur[0];
   return 0;
@@ -379,8 +406,9 @@ int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* 
     if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_RHO0, 2));
     PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, r, S_RHO0, S_RHO0, 1, 1));
   } else {
-    PDE_OK(mg->vcycle(c, A, r, &z));
-    PDE_OK(launch_dot(c, g, nc, r, z, S_RHO0));
+    bool fused = false;
+    PDE_OK(mg->vcycle(c, A, r, &z, S_RHO0, &fused));
+    if (!fused) PDE_OK(launch_dot(c, g, nc, r, z, S_RHO0));
     PDE_OK(launch_dot(c, g, nc, r, r, S_RHO0 + 1));
     if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_RHO0, 2));
     PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, z, S_RHO0, S_RHO0, 1, 0));
@@ -406,8 +434,9 @@ int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* 
     PDE_OK(launch_cg_update(c, g, A.dev, x, r, w.p.p, w.q.p, sr, S_XY, sn, sn + 1, !gmg));
     if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 2));
     if (gmg) {
-      PDE_OK(mg->vcycle(c, A, r, &z));
-      PDE_OK(launch_dot(c, g, nc, r, z, sn));
+      bool fused = false;
+      PDE_OK(mg->vcycle(c, A, r, &z, sn, &fused));
+      if (!fused) PDE_OK(launch_dot(c, g, nc, r, z, sn));
       if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 1));
     }
     PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, gmg ? z : r, sr, sn, 0, !gmg));

@@ -41,7 +41,9 @@ struct Hierarchy {
   // build levels 1.. from a fine operator description; level 0 uses the caller's operator
   int build(pde_ctx* c, const Operator& fine, int kind, double p0, double p1);
   // z = V(b0) ; returns pointer to the buffer holding z (one of level-0 xa/xb)
-  int vcycle(pde_ctx* c, const Operator& fine, const double* b0, double** z_out);
+  // dot_slot >= 0: the last smoother sweep also leaves sum b0.z in that scalar slot if it can (*dot_done)
+  int vcycle(pde_ctx* c, const Operator& fine, const double* b0, double** z_out, int dot_slot = -1,
+             bool* dot_done = nullptr);
   int levels() const { return (int)lv.size(); }
   void release();
 };

@@ -70,7 +70,7 @@ struct SweepArgs {
   double* y;
   double* d;
   double bconst[3];
-  double bscale, ascale, c1, c2;
+  double bscale, ascale, c1, c2, s0;
   double load_int;    // load of the interior class
   double dinv_int[3]; // Jacobi diagonal inverse of the interior class
   int do_reduce;
@@ -150,12 +150,19 @@ __device__ __noinline__ RowVal<NC> slow_row(const Grid& g, const double* __restr
   return r;
 }
 
-template <int NC, int YS, bool CHEBY, bool HAS_B>
+// MODE: 0 apply (B = bconst*load), 1 residual-type (B from field b), 2 Chebyshev sweep, 3 fused first TWO
+// Chebyshev sweeps from a zero guess (input field = right-hand side; needs a uniform Jacobi diagonal)
+enum { M_APPLY = 0, M_RESID = 1, M_CHEBY = 2, M_FIRST2 = 3 };
+
+template <int NC, int YS, int MODE>
 __global__ void __launch_bounds__(NC == 1 ? 384 : 256)
 k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
           const __grid_constant__ Coef<NC> C, const double* __restrict__ coef, const double* __restrict__ dinv,
           const double* __restrict__ load, const __grid_constant__ SweepArgs a, const __grid_constant__ SweepGeom sw,
           ReduceBuf red, double* red_out) {
+  constexpr bool CHEBY = MODE >= M_CHEBY;
+  constexpr bool HAS_B = MODE == M_RESID || MODE == M_CHEBY;
+  constexpr bool LOAD_D = MODE == M_CHEBY;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stage0 = reinterpret_cast<double*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SW_STAGES * sw.stage_elems * sizeof(double));
@@ -242,17 +249,17 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
     const int zout = za + i - 2;
     // early global loads for the retiring outputs (consumed after the stencil arithmetic)
     double bv[YS][NC], dv[YS][NC];
-    if (FIN && (HAS_B || CHEBY)) {
+    if (FIN && (HAS_B || LOAD_D)) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const double* __restrict__ bp = HAS_B ? a.b + (long long)g.plane * zout + c * g.comp_stride : nullptr;
-        const double* __restrict__ dp = CHEBY ? a.d + (long long)g.plane * zout + c * g.comp_stride : nullptr;
+        const double* __restrict__ dp = LOAD_D ? a.d + (long long)g.plane * zout + c * g.comp_stride : nullptr;
 #pragma unroll
         for (int j = 0; j < YS; ++j) {
           const bool ok = (valid >> j) & 1u;
           const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
           if (HAS_B) bv[j][c] = ok ? bp[off] : 0.0;
-          if (CHEBY) dv[j][c] = ok ? dp[off] : 0.0;
+          if (LOAD_D) dv[j][c] = ok ? dp[off] : 0.0;
         }
       }
     }
@@ -306,9 +313,12 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
             const long long ii = idx + c * g.comp_stride;
             const double B = HAS_B ? bv[j][c] : a.bconst[c] * ld;
             if (CHEBY) {
+              // (M_FIRST2 never reaches here: it requires all faces Dirichlet, so no slow rows exist)
               const double dn = a.c1 * dv[j][c] + a.c2 * __ldg(dinv + cls * NC + c) * (B - rv.v[c]);
               a.d[ii] = dn;
-              a.y[ii] = xprev[j][c] + dn;
+              const double yv = xprev[j][c] + dn;
+              a.y[ii] = yv;
+              red_xy = fma(B, yv, red_xy);
             } else {
               const double yv = a.bscale * B + a.ascale * rv.v[c];
               if (a.y) a.y[ii] = yv;
@@ -326,15 +336,26 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
         double* __restrict__ yp = a.y ? a.y + pbase + c * g.comp_stride : nullptr;
         const double bB = a.bscale * a.bconst[c] * a.load_int;  // constant load term of the interior class
         const double c2d = a.c2 * a.dinv_int[c];
+        const double s0d = a.s0 * a.dinv_int[c];
 #pragma unroll
         for (int j = 0; j < YS; ++j) {
           const bool on = (todo >> j) & 1u;
           const double m = on ? mrow[j] * mz : 0.0;
           const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
-          if (CHEBY) {
-            const double B = HAS_B ? bv[j][c] : a.bconst[c] * a.load_int;
+          if (MODE == M_FIRST2) {
+            // zero guess: x1 = d1 = s0 D^-1 b ; r = b - A x1 = b - s0 D^-1 (A b) ; d2 = c1 d1 + c2 D^-1 r
+            const double bi = xprev[j][c];
+            const double d1 = s0d * bi;
+            const double dn = m * fma(a.c1, d1, c2d * fma(-s0d, aP[j][c], bi));
+            const double yv = m * d1 + dn;
+            if (on) { dp[off] = dn; yp[off] = yv; }
+            red_xy = fma(bi, yv, red_xy);
+          } else if (CHEBY) {
+            const double B = bv[j][c];
             const double dn = m * fma(a.c1, dv[j][c], c2d * (B - aP[j][c]));
-            if (on) { dp[off] = dn; yp[off] = xprev[j][c] + dn; }
+            const double yv = xprev[j][c] + dn;
+            if (on) { dp[off] = dn; yp[off] = yv; }
+            red_xy = fma(m * B, yv, red_xy);
           } else {
             const double yv = m * (HAS_B ? fma(a.ascale, aP[j][c], a.bscale * bv[j][c]) : fma(a.ascale, aP[j][c], bB));
             if (on && yp) yp[off] = yv;
@@ -357,9 +378,14 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
     if (i + 2 < nplanes) body(T_{}, i + 2, accB, accC, accA, xA, xB);
   }
 
-  if (!CHEBY && a.do_reduce) {
-    double v[2] = {red_xy, red_yy};
-    block_reduce_finalize<2>(v, red, red_out);
+  if (a.do_reduce) {
+    if (CHEBY) {  // sum b.y of a smoother sweep (the preconditioned-CG r.z)
+      double v[1] = {red_xy};
+      block_reduce_finalize<1>(v, red, red_out);
+    } else {
+      double v[2] = {red_xy, red_yy};
+      block_reduce_finalize<2>(v, red, red_out);
+    }
   }
 }
 
@@ -436,7 +462,7 @@ static const SweepTune& sweep_tune() {
   return t;
 }
 
-template <int NC, int YS, bool CHEBY, bool HAS_B>
+template <int NC, int YS, int MODE>
 static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
   const SweepTune& tu = sweep_tune();
   SweepGeom sw;
@@ -460,6 +486,8 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   sw.by = sw.ty + 2;
   if (sw.bx > 256 || sw.by > 256) PDE_FAIL("sweep TMA box exceeds 256");
   int zc = tu.zc < 2 ? 2 : tu.zc;
+  // small grids (coarse multigrid levels): shorter z chunks so that the grid still covers the SMs
+  while (zc > 4 && (long long)sw.ntx * sw.nty * ((g.nzl + zc - 1) / zc) < 4LL * c->sm_count) zc /= 2;
   sw.nzc = (g.nzl + zc - 1) / zc;
   sw.zc = (g.nzl + sw.nzc - 1) / sw.nzc;
   sw.nzc = (g.nzl + sw.zc - 1) / sw.zc;
@@ -467,7 +495,7 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   const long long items = (long long)sw.ntx * sw.nty * sw.nzc;
   if (items > RED_MAX_BLOCKS) PDE_FAIL("sweep grid exceeds the reduction buffer");
   const size_t smem = (size_t)SW_STAGES * sw.stage_elems * sizeof(double) + SW_STAGES * sizeof(uint64_t);
-  auto kern = k_sweep3d<NC, YS, CHEBY, HAS_B>;
+  auto kern = k_sweep3d<NC, YS, MODE>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -481,7 +509,7 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   SweepArgs sa;
   sa.x = a.x; sa.b = a.b; sa.y = a.y; sa.d = a.d;
   for (int i = 0; i < 3; ++i) sa.bconst[i] = a.bconst[i];
-  sa.bscale = a.bscale; sa.ascale = a.ascale; sa.c1 = a.c1; sa.c2 = a.c2;
+  sa.bscale = a.bscale; sa.ascale = a.ascale; sa.c1 = a.c1; sa.c2 = a.c2; sa.s0 = a.s0;
   sa.load_int = op.h_load_int;
   for (int i = 0; i < 3; ++i) sa.dinv_int[i] = i < NC ? op.h_dinv_int[i] : 0.0;
   sa.do_reduce = a.reduce_slot_xy >= 0;
@@ -502,13 +530,14 @@ int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev&
   if ((long long)g.nn[0] * g.nn[1] * g.nzl < 4096) return 0;
   const int ys = sweep_tune().ys;
   *handled = true;
-#define SWEEP_DISPATCH(NC_, YS_)                                                                          \
-  do {                                                                                                   \
-    if (a.cheby) return a.b ? launch_sweep_t<NC_, YS_, true, true>(c, g, bc, op, a)                       \
-                            : launch_sweep_t<NC_, YS_, true, false>(c, g, bc, op, a);                     \
-    return a.b ? launch_sweep_t<NC_, YS_, false, true>(c, g, bc, op, a)                                   \
-               : launch_sweep_t<NC_, YS_, false, false>(c, g, bc, op, a);                                 \
+#define SWEEP_DISPATCH(NC_, YS_)                                                          \
+  do {                                                                                   \
+    if (a.cheby == 2) return launch_sweep_t<NC_, YS_, M_FIRST2>(c, g, bc, op, a);        \
+    if (a.cheby) return launch_sweep_t<NC_, YS_, M_CHEBY>(c, g, bc, op, a);              \
+    return a.b ? launch_sweep_t<NC_, YS_, M_RESID>(c, g, bc, op, a)                      \
+               : launch_sweep_t<NC_, YS_, M_APPLY>(c, g, bc, op, a);                     \
   } while (0)
+  if (a.cheby == 1 && !a.b) { *handled = false; return 0; }  // smoother sweeps always carry a rhs field
   if (op.ncomp == 1) {
     if (ys == 2) SWEEP_DISPATCH(1, 2);
     SWEEP_DISPATCH(1, 4);
