@@ -187,6 +187,8 @@ int launch_dot(pde_ctx* c, const Grid& g, int ncomp, const double* a, const doub
 int launch_zero(pde_ctx* c, const Grid& g, int ncomp, double* a);
 int launch_copy(pde_ctx* c, const Grid& g, int ncomp, double* dst, const double* src);
 int launch_axpy(pde_ctx* c, const Grid& g, int ncomp, double* y, const double* x, double alpha);
+// e = u - uold ; uold = u ; u = u + e
+int launch_extrapolate(pde_ctx* c, const Grid& g, int ncomp, double* u, double* uold, double* e);
 // first Chebyshev sweep from a zero guess: d = s*dinv*b ; x = d
 int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* b, double* d,
                        double* x, double s);

@@ -306,6 +306,31 @@ k_axpy(double* __restrict__ y, const double* __restrict__ x, double alpha, long 
   }
 }
 
+__global__ void __launch_bounds__(256)
+k_extrapolate(double* __restrict__ u, double* __restrict__ uold, double* __restrict__ e, long long n, int ncomp,
+              long long cs) {
+  const long long n2 = n >> 1;
+  for (int cidx = 0; cidx < ncomp; ++cidx) {
+    double2* u2 = reinterpret_cast<double2*>(u + cidx * cs);
+    double2* o2 = reinterpret_cast<double2*>(uold + cidx * cs);
+    double2* e2 = reinterpret_cast<double2*>(e + cidx * cs);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+      const double2 a = u2[i], b = o2[i];
+      const double2 d = make_double2(a.x - b.x, a.y - b.y);
+      e2[i] = d;
+      o2[i] = a;
+      u2[i] = make_double2(a.x + d.x, a.y + d.y);
+    }
+  }
+}
+int launch_extrapolate(pde_ctx* c, const Grid& g, int ncomp, double* u, double* uold, double* e) {
+  int blocks = flat_blocks(c, g.total / 2, 256 * 4);
+  k_extrapolate<<<blocks, 256, 0, c->stream>>>(u, uold, e, g.total, ncomp, g.comp_stride);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_dot(pde_ctx* c, const Grid& g, int ncomp, const double* a, const double* b, int slot) {
   int blocks = flat_blocks(c, g.total / 2, 256 * 4);
   k_dot<<<blocks, 256, 0, c->stream>>>(a, b, g.total, ncomp, g.comp_stride, c->red, c->scal + slot);

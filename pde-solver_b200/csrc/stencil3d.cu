@@ -16,6 +16,8 @@
 //   27-class table when they retire; Dirichlet rows are masked.
 #include <cuda.h>
 
+#include <cmath>
+
 #include <map>
 #include <mutex>
 #include <type_traits>
@@ -76,51 +78,74 @@ struct SweepArgs {
   int do_reduce;
 };
 
-// acc[i] += sum_j C[k][i][j] * v[j]
-template <int NC>
+// acc[i] += sum_j C[k][i][j] * v[j].  OFFD: the block has a structurally zero diagonal (elasticity blocks of
+// the face- and body-diagonal offsets couple different components only), so those products are skipped.
+template <int NC, bool OFFD>
 __device__ __forceinline__ void blk_fma(double (&acc)[NC], const Coef<NC>& C, int k, const double (&v)[NC]) {
 #pragma unroll
   for (int i = 0; i < NC; ++i)
 #pragma unroll
-    for (int j = 0; j < NC; ++j) acc[i] = fma(C.c[k][i * NC + j], v[j], acc[i]);
+    for (int j = 0; j < NC; ++j)
+      if (!(OFFD && i == j)) acc[i] = fma(C.c[k][i * NC + j], v[j], acc[i]);
 }
-template <int NC>
+template <int NC, bool OFFD>
 __device__ __forceinline__ void blk_set(double (&acc)[NC], const Coef<NC>& C, int k, const double (&v)[NC]) {
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
-    acc[i] = C.c[k][i * NC] * v[0];
+    bool first = true;
+    acc[i] = 0.0;
 #pragma unroll
-    for (int j = 1; j < NC; ++j) acc[i] = fma(C.c[k][i * NC + j], v[j], acc[i]);
+    for (int j = 0; j < NC; ++j) {
+      if (OFFD && i == j) continue;
+      acc[i] = first ? C.c[k][i * NC + j] * v[j] : fma(C.c[k][i * NC + j], v[j], acc[i]);
+      first = false;
+    }
   }
 }
 
 // One resident plane: V[r][c] = plane values at strip rows r-1 (r = 0..YS+1), columns c-1 (c = 0..2).
 //   aP (output one plane below) gets the dz=+1 part, a0 the in-plane part, aM (output one plane above)
 //   is started with the dz=-1 part.
+// Vector operators (NC > 1): the block at -d equals the block at +d (each block is symmetric and the
+// operator is symmetric), so the in-plane neighbour pairs are summed before the block product.
 template <int NC, int YS>
 __device__ __forceinline__ void plane_contrib(const Coef<NC>& C, const double (&V)[YS + 2][3][NC],
                                               double (&aP)[YS][NC], double (&a0)[YS][NC], double (&aM)[YS][NC]) {
+  constexpr bool VEC = NC > 1;
 #pragma unroll
   for (int j = 0; j < YS; ++j) {
     const int r = j + 1;
-    // in-plane: centre, +x, -x, +y, -y, (+x,+y), (-x,-y)
-    blk_fma<NC>(a0[j], C, 0, V[r][1]);
-    blk_fma<NC>(a0[j], C, 1, V[r][2]);
-    blk_fma<NC>(a0[j], C, 2, V[r][0]);
-    blk_fma<NC>(a0[j], C, 3, V[r + 1][1]);
-    blk_fma<NC>(a0[j], C, 4, V[r - 1][1]);
-    blk_fma<NC>(a0[j], C, 7, V[r + 1][2]);
-    blk_fma<NC>(a0[j], C, 8, V[r - 1][0]);
+    // in-plane: centre, +-x, +-y, +-(x,y)
+    blk_fma<NC, false>(a0[j], C, 0, V[r][1]);
+    if (VEC) {
+      double sx[NC], sy[NC], sd[NC];
+#pragma unroll
+      for (int q = 0; q < NC; ++q) {
+        sx[q] = V[r][2][q] + V[r][0][q];
+        sy[q] = V[r + 1][1][q] + V[r - 1][1][q];
+        sd[q] = V[r + 1][2][q] + V[r - 1][0][q];
+      }
+      blk_fma<NC, false>(a0[j], C, 1, sx);
+      blk_fma<NC, false>(a0[j], C, 3, sy);
+      blk_fma<NC, true>(a0[j], C, 7, sd);
+    } else {
+      blk_fma<NC, false>(a0[j], C, 1, V[r][2]);
+      blk_fma<NC, false>(a0[j], C, 2, V[r][0]);
+      blk_fma<NC, false>(a0[j], C, 3, V[r + 1][1]);
+      blk_fma<NC, false>(a0[j], C, 4, V[r - 1][1]);
+      blk_fma<NC, false>(a0[j], C, 7, V[r + 1][2]);
+      blk_fma<NC, false>(a0[j], C, 8, V[r - 1][0]);
+    }
     // this plane is dz=+1 for the output below: (0,0,1), (1,0,1), (0,1,1), (1,1,1)
-    blk_fma<NC>(aP[j], C, 5, V[r][1]);
-    blk_fma<NC>(aP[j], C, 9, V[r][2]);
-    blk_fma<NC>(aP[j], C, 11, V[r + 1][1]);
-    blk_fma<NC>(aP[j], C, 13, V[r + 1][2]);
+    blk_fma<NC, false>(aP[j], C, 5, V[r][1]);
+    blk_fma<NC, VEC>(aP[j], C, 9, V[r][2]);
+    blk_fma<NC, VEC>(aP[j], C, 11, V[r + 1][1]);
+    blk_fma<NC, VEC>(aP[j], C, 13, V[r + 1][2]);
     // this plane is dz=-1 for the output above: (0,0,-1), (-1,0,-1), (0,-1,-1), (-1,-1,-1)
-    blk_set<NC>(aM[j], C, 6, V[r][1]);
-    blk_fma<NC>(aM[j], C, 10, V[r][0]);
-    blk_fma<NC>(aM[j], C, 12, V[r - 1][1]);
-    blk_fma<NC>(aM[j], C, 14, V[r - 1][0]);
+    blk_set<NC, false>(aM[j], C, 6, V[r][1]);
+    blk_fma<NC, VEC>(aM[j], C, 10, V[r][0]);
+    blk_fma<NC, VEC>(aM[j], C, 12, V[r - 1][1]);
+    blk_fma<NC, VEC>(aM[j], C, 14, V[r - 1][0]);
   }
 }
 
@@ -163,6 +188,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
   constexpr bool CHEBY = MODE >= M_CHEBY;
   constexpr bool HAS_B = MODE == M_RESID || MODE == M_CHEBY;
   constexpr bool LOAD_D = MODE == M_CHEBY;
+  constexpr bool XQ_REG = NC == 1;  // own-column queue in registers; vector kernels re-read x (L2 hit) instead
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stage0 = reinterpret_cast<double*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)SW_STAGES * sw.stage_elems * sizeof(double));
@@ -248,20 +274,28 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
     const uint32_t parity = (uint32_t)((i / SW_STAGES) & 1);
     const int zout = za + i - 2;
     // early global loads for the retiring outputs (consumed after the stencil arithmetic)
-    double bv[YS][NC], dv[YS][NC];
-    if (FIN && (HAS_B || LOAD_D)) {
+    double bv[YS][NC], dv[YS][NC], xv[YS][NC];
+    if (FIN && (HAS_B || LOAD_D || !XQ_REG)) {
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const double* __restrict__ bp = HAS_B ? a.b + (long long)g.plane * zout + c * g.comp_stride : nullptr;
         const double* __restrict__ dp = LOAD_D ? a.d + (long long)g.plane * zout + c * g.comp_stride : nullptr;
+        const double* __restrict__ xp = a.x + (long long)g.plane * zout + c * g.comp_stride;
 #pragma unroll
         for (int j = 0; j < YS; ++j) {
           const bool ok = (valid >> j) & 1u;
           const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
           if (HAS_B) bv[j][c] = ok ? bp[off] : 0.0;
           if (LOAD_D) dv[j][c] = ok ? dp[off] : 0.0;
+          if (!XQ_REG) xv[j][c] = ok ? xp[off] : 0.0;
         }
       }
+    }
+    if (FIN && XQ_REG) {
+#pragma unroll
+      for (int j = 0; j < YS; ++j)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) xv[j][c] = xprev[j][c];
     }
     mbar_wait(bar0 + 8 * stage, parity);
     {
@@ -279,10 +313,12 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
             for (int q = 0; q < NC; ++q) V[r][c][q] = sp[q * comp_elems + r * sw.bx + c];
           }
         }
+      if (XQ_REG) {
 #pragma unroll
-      for (int j = 0; j < YS; ++j)
+        for (int j = 0; j < YS; ++j)
 #pragma unroll
-        for (int q = 0; q < NC; ++q) xcur[j][q] = V[j + 1][1][q];
+          for (int q = 0; q < NC; ++q) xcur[j][q] = V[j + 1][1][q];
+      }
       plane_contrib<NC, YS>(C, V, aP, a0, aM);
     }
     __syncthreads();  // every thread has consumed this stage
@@ -316,13 +352,13 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
               // (M_FIRST2 never reaches here: it requires all faces Dirichlet, so no slow rows exist)
               const double dn = a.c1 * dv[j][c] + a.c2 * __ldg(dinv + cls * NC + c) * (B - rv.v[c]);
               a.d[ii] = dn;
-              const double yv = xprev[j][c] + dn;
+              const double yv = xv[j][c] + dn;
               a.y[ii] = yv;
               red_xy = fma(B, yv, red_xy);
             } else {
               const double yv = a.bscale * B + a.ascale * rv.v[c];
               if (a.y) a.y[ii] = yv;
-              red_xy = fma(xprev[j][c], yv, red_xy);
+              red_xy = fma(xv[j][c], yv, red_xy);
               red_yy = fma(yv, yv, red_yy);
             }
           }
@@ -344,7 +380,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
           const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
           if (MODE == M_FIRST2) {
             // zero guess: x1 = d1 = s0 D^-1 b ; r = b - A x1 = b - s0 D^-1 (A b) ; d2 = c1 d1 + c2 D^-1 r
-            const double bi = xprev[j][c];
+            const double bi = xv[j][c];
             const double d1 = s0d * bi;
             const double dn = m * fma(a.c1, d1, c2d * fma(-s0d, aP[j][c], bi));
             const double yv = m * d1 + dn;
@@ -353,13 +389,13 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
           } else if (CHEBY) {
             const double B = bv[j][c];
             const double dn = m * fma(a.c1, dv[j][c], c2d * (B - aP[j][c]));
-            const double yv = xprev[j][c] + dn;
+            const double yv = xv[j][c] + dn;
             if (on) { dp[off] = dn; yp[off] = yv; }
             red_xy = fma(m * B, yv, red_xy);
           } else {
             const double yv = m * (HAS_B ? fma(a.ascale, aP[j][c], a.bscale * bv[j][c]) : fma(a.ascale, aP[j][c], bB));
             if (on && yp) yp[off] = yv;
-            red_xy = fma(xprev[j][c], yv, red_xy);
+            red_xy = fma(xv[j][c], yv, red_xy);
             red_yy = fma(yv, yv, red_yy);
           }
         }
@@ -543,6 +579,17 @@ int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev&
     SWEEP_DISPATCH(1, 4);
   }
   if (op.ncomp == 3) {
+    // the vector kernel relies on block(+d) == block(-d) for the in-plane pairs and on zero diagonals of the
+    // face-/body-diagonal blocks (both structural for P1 elasticity on the Kuhn split); verify, else generic
+    double mx = 0;
+    for (int q = 0; q < PDE_NOFF * 9; ++q) mx = fmax(mx, fabs(op.h_int[q]));
+    bool ok = true;
+    const int pairs[3][2] = {{1, 2}, {3, 4}, {7, 8}};
+    for (auto& pr : pairs)
+      for (int q = 0; q < 9; ++q) ok = ok && fabs(op.h_int[pr[0] * 9 + q] - op.h_int[pr[1] * 9 + q]) <= 1e-12 * mx;
+    for (int k = 7; k < PDE_NOFF; ++k)
+      for (int i = 0; i < 3; ++i) ok = ok && fabs(op.h_int[k * 9 + i * 3 + i]) <= 1e-12 * mx;
+    if (!ok) { *handled = false; return 0; }
     if (ys == 1) SWEEP_DISPATCH(3, 1);
     SWEEP_DISPATCH(3, 2);
   }
