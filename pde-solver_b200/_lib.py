@@ -6,7 +6,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpde_b200.so")
+LIB_PATH = os.environ.get("PDE_B200_LIB") or os.path.join(_HERE, "libpde_b200.so")  # override: A/B kernel builds
 
 
 class PdeError(RuntimeError):

@@ -33,6 +33,7 @@ struct SweepGeom {
   int zc;             // planes per chunk
   int ns;             // strips (of YS rows) per tile
   int stage_elems;    // doubles per stage (all components), multiple of 16
+  int spec;           // 1: the last warp is a dedicated TMA producer (empty/full mbarriers, no CTA barrier)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -42,6 +43,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -179,7 +183,7 @@ __device__ __noinline__ RowVal<NC> slow_row(const Grid& g, const double* __restr
 // Chebyshev sweeps from a zero guess (input field = right-hand side; needs a uniform Jacobi diagonal)
 enum { M_APPLY = 0, M_RESID = 1, M_CHEBY = 2, M_FIRST2 = 3 };
 
-template <int NC, int YS, int MODE>
+template <int NC, int YS, int MODE, bool SPEC>
 __global__ void __launch_bounds__(NC == 1 ? 384 : 256)
 k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
           const __grid_constant__ Coef<NC> C, const double* __restrict__ coef, const double* __restrict__ dinv,
@@ -207,19 +211,44 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
   const uint32_t stg0 = smem_u32(stage0);
   const uint32_t stage_stride = (uint32_t)(sw.stage_elems * sizeof(double));
 
+  // warp specialisation: the LAST warp of the CTA only feeds the TMA ring; the others compute.
+  //   full[s]  : TMA transaction barrier of stage s (1 arrival + bytes)
+  //   empty[s] : one arrival per compute warp once it has read stage s
+  constexpr bool spec = SPEC;
+  const int ncw = (int)(blockDim.x >> 5) - (spec ? 1 : 0);  // compute warps
+  const uint32_t ebar0 = bar0 + 8 * SW_STAGES;
   if (t == 0) {
 #pragma unroll
-    for (int s = 0; s < SW_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+    for (int s = 0; s < SW_STAGES; ++s) {
+      mbar_init(bar0 + 8 * s, 1);
+      mbar_init(ebar0 + 8 * s, (uint32_t)ncw);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (t == 0) {
+  if (!spec && t == 0) {
     for (int i = 0; i < SW_STAGES && i < nplanes; ++i) {
       mbar_expect_tx(bar0 + 8 * i, stage_bytes);
-      // tensor z coordinate: ghost plane is z=0, local plane lz is z=lz+1.  The box starts at x0-2: TMA
-      // needs the inner start coordinate 16-byte aligned (even for FP64); x0-1 raises an illegal-instruction fault
       tma_load_4d(stg0 + i * stage_stride, &tmx, x0 - 2, y0 - 1, za + i, 0, bar0 + 8 * i);
     }
+  }
+  if (spec && (t >> 5) == ncw) {
+    // ---- producer warp ----
+    if ((t & 31) == 0) {
+      for (int i = 0; i < nplanes; ++i) {
+        const int stage = i % SW_STAGES;
+        if (i >= SW_STAGES) mbar_wait(ebar0 + 8 * stage, (uint32_t)(((i / SW_STAGES) - 1) & 1));
+        mbar_expect_tx(bar0 + 8 * stage, stage_bytes);
+        // tensor z coordinate: ghost plane is z=0, local plane lz is z=lz+1.  The box starts at x0-2: TMA needs
+        // the inner start coordinate 16-byte aligned (even for FP64); x0-1 raises an illegal-instruction fault
+        tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i, 0, bar0 + 8 * stage);
+      }
+    }
+    if (a.do_reduce) {  // the block reduction below is CTA-wide
+      if (MODE >= M_CHEBY) { double v[1] = {0.0}; block_reduce_finalize<1>(v, red, red_out); }
+      else { double v[2] = {0.0, 0.0}; block_reduce_finalize<2>(v, red, red_out); }
+    }
+    return;
   }
 
   const int lx = t % sw.tx;
@@ -321,10 +350,15 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
       }
       plane_contrib<NC, YS>(C, V, aP, a0, aM);
     }
-    __syncthreads();  // every thread has consumed this stage
-    if (t == 0 && i + SW_STAGES < nplanes) {
-      mbar_expect_tx(bar0 + 8 * stage, stage_bytes);
-      tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i + SW_STAGES, 0, bar0 + 8 * stage);
+    if (spec) {
+      __syncwarp();  // this warp has consumed the stage: hand it back to the producer
+      if ((t & 31) == 0) mbar_arrive(ebar0 + 8 * stage);
+    } else {
+      __syncthreads();  // every thread has consumed this stage
+      if (t == 0 && i + SW_STAGES < nplanes) {
+        mbar_expect_tx(bar0 + 8 * stage, stage_bytes);
+        tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i + SW_STAGES, 0, bar0 + 8 * stage);
+      }
     }
     if (FIN) {
       const int gz = zout + g.z0;
@@ -490,26 +524,29 @@ static int env_int(const char* name, int dflt) {
 }
 
 struct SweepTune {
-  int nt, zc, ys, txmax;
+  int nt, zc, ys, txmax, spec;
 };
 static const SweepTune& sweep_tune() {
-  static SweepTune t = {env_int("PDE_B200_SW_NT", 192), env_int("PDE_B200_SW_ZC", 64), env_int("PDE_B200_SW_YS", 0),
-                        env_int("PDE_B200_SW_TXMAX", 192)};
+  static SweepTune t = {env_int("PDE_B200_SW_NT", 0), env_int("PDE_B200_SW_ZC", 64), env_int("PDE_B200_SW_YS", 0),
+                        env_int("PDE_B200_SW_TXMAX", 0), env_int("PDE_B200_SW_SPEC", -1)};
   return t;
 }
 
-template <int NC, int YS, int MODE>
+template <int NC, int YS, int MODE, bool SPEC>
 static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
   const SweepTune& tu = sweep_tune();
   SweepGeom sw;
-  int txmax = tu.txmax < 32 ? 32 : (tu.txmax > 254 ? 254 : tu.txmax);
-  if (txmax > (NC == 1 ? 384 : 256) - 2) txmax = (NC == 1 ? 384 : 256) - 2;
+  sw.spec = SPEC ? 1 : 0;
+  int txmax = tu.txmax > 0 ? tu.txmax : (NC == 1 ? 192 : 64);  // tuned on B200: heat 512^3, elasticity 1280x256x256
+  txmax = txmax < 32 ? 32 : (txmax > 254 ? 254 : txmax);
+  if (txmax > (NC == 1 ? 384 : 256) - 34) txmax = (NC == 1 ? 384 : 256) - 34;
   sw.ntx = (g.nn[0] + txmax - 1) / txmax;
   sw.tx = (g.nn[0] + sw.ntx - 1) / sw.ntx;
   sw.tx += sw.tx & 1;  // even: the TMA box row must be a multiple of 16 bytes
   sw.ntx = (g.nn[0] + sw.tx - 1) / sw.tx;
-  const int maxnt = NC == 1 ? 384 : 256;
-  int nt_target = tu.nt < 64 ? 64 : (tu.nt > maxnt ? maxnt : tu.nt);
+  const int maxnt = (NC == 1 ? 384 : 256) - (SPEC ? 32 : 0);  // a producer warp is extra
+  int nt_target = tu.nt > 0 ? tu.nt : (NC == 1 ? 192 : 128);
+  nt_target = nt_target < 64 ? 64 : (nt_target > maxnt ? maxnt : nt_target);
   sw.ns = nt_target / sw.tx;
   if (sw.ns < 1) sw.ns = 1;
   const int max_ns = (g.nn[1] + YS - 1) / YS;
@@ -530,8 +567,8 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   sw.stage_elems = ((sw.bx * sw.by * NC + 15) / 16) * 16;
   const long long items = (long long)sw.ntx * sw.nty * sw.nzc;
   if (items > RED_MAX_BLOCKS) PDE_FAIL("sweep grid exceeds the reduction buffer");
-  const size_t smem = (size_t)SW_STAGES * sw.stage_elems * sizeof(double) + SW_STAGES * sizeof(uint64_t);
-  auto kern = k_sweep3d<NC, YS, MODE>;
+  const size_t smem = (size_t)SW_STAGES * sw.stage_elems * sizeof(double) + 2 * SW_STAGES * sizeof(uint64_t);
+  auto kern = k_sweep3d<NC, YS, MODE, SPEC>;
   static size_t smem_set = 0;
   if (smem > smem_set) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -550,7 +587,7 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   for (int i = 0; i < 3; ++i) sa.dinv_int[i] = i < NC ? op.h_dinv_int[i] : 0.0;
   sa.do_reduce = a.reduce_slot_xy >= 0;
   double* out = sa.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
-  kern<<<(unsigned)items, nt, smem, c->stream>>>(tm, g, bc, C, op.coef, op.dinv, op.load, sa, sw, c->red, out);
+  kern<<<(unsigned)items, nt + (sw.spec ? 32 : 0), smem, c->stream>>>(tm, g, bc, C, op.coef, op.dinv, op.load, sa, sw, c->red, out);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -566,12 +603,19 @@ int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev&
   if ((long long)g.nn[0] * g.nn[1] * g.nzl < 4096) return 0;
   const int ys = sweep_tune().ys;
   *handled = true;
-#define SWEEP_DISPATCH(NC_, YS_)                                                          \
+#define SWEEP_DISPATCH_S(NC_, YS_, SP_)                                                   \
   do {                                                                                   \
-    if (a.cheby == 2) return launch_sweep_t<NC_, YS_, M_FIRST2>(c, g, bc, op, a);        \
-    if (a.cheby) return launch_sweep_t<NC_, YS_, M_CHEBY>(c, g, bc, op, a);              \
-    return a.b ? launch_sweep_t<NC_, YS_, M_RESID>(c, g, bc, op, a)                      \
-               : launch_sweep_t<NC_, YS_, M_APPLY>(c, g, bc, op, a);                     \
+    if (a.cheby == 2) return launch_sweep_t<NC_, YS_, M_FIRST2, SP_>(c, g, bc, op, a);   \
+    if (a.cheby) return launch_sweep_t<NC_, YS_, M_CHEBY, SP_>(c, g, bc, op, a);         \
+    return a.b ? launch_sweep_t<NC_, YS_, M_RESID, SP_>(c, g, bc, op, a)                 \
+               : launch_sweep_t<NC_, YS_, M_APPLY, SP_>(c, g, bc, op, a);                \
+  } while (0)
+  // PDE_B200_SW_SPEC=1: dedicated TMA producer warp (measured slower than the CTA-barrier ring for both
+  // operators on B200, kept selectable)
+#define SWEEP_DISPATCH(NC_, YS_)                              \
+  do {                                                       \
+    if (sweep_tune().spec > 0) SWEEP_DISPATCH_S(NC_, YS_, true); \
+    SWEEP_DISPATCH_S(NC_, YS_, false);                       \
   } while (0)
   if (a.cheby == 1 && !a.b) { *handled = false; return 0; }  // smoother sweeps always carry a rhs field
   if (op.ncomp == 1) {
