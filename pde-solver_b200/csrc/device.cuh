@@ -68,7 +68,7 @@ __device__ __forceinline__ long long kOffDdev(int k, int PX, long long plane) {
 // deterministic two-stage reduction: per-block partials, last block sums them in fixed order
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-template <int NV>
+template <int NV, bool ACC = false>
 __device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], ReduceBuf red, double* out) {
   __shared__ double sm[NV][32];
   __shared__ bool is_last;
@@ -113,7 +113,7 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], ReduceBuf
       double t = lane < nwarp ? sm[i][lane] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-      if (lane == 0) out[i] = t;
+      if (lane == 0) out[i] = ACC ? out[i] + t : t;
     }
   }
   if (tid == 0) *red.counter = 0u;
@@ -177,6 +177,8 @@ struct StencilArgs {
 };
 
 int launch_stencil(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
+// rows of the non-Dirichlet nodes on the domain faces (class-table stencil); reductions are ADDED to the slot
+int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
 // Jacobi-PCG fused update: x += a p, r -= a q, rho_new = r.dinv r, rr = r.r  (a = rho/pAp from scal)
 int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, double* r, const double* p,
                      const double* q, int slot_rho, int slot_pap, int slot_rho_new, int slot_rr, int jacobi);

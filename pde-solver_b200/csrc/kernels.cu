@@ -8,6 +8,8 @@
 //   k_cell_rhs       : von-Mises / axial stress-strain load of project(eq_expr, Vs) (:1541-1546,
 //                      1691-1714, 1841-1862)
 //   k_mesh_*         : IntervalMesh/RectangleMesh/BoxMesh + P1 dof maps (:229-230, 369-370, 533-535)
+#include <cstring>
+
 #include "device.cuh"
 
 // ----------------------------------------------------------------------------------------------
@@ -238,6 +240,134 @@ k_cg_pupdate(const __grid_constant__ Grid g, const double* __restrict__ dinv, do
     case 3: { constexpr int NC = 3; CALL; } break;  \
     default: PDE_FAIL("unsupported component count"); \
   }
+
+// ----------------------------------------------------------------------------------------------
+// face rows: the non-Dirichlet nodes on the faces of the box have incomplete element patches, so their
+// stencil coefficients come from the 27-class table.  The streaming kernel (stencil3d.cu) skips them;
+// this kernel computes them right after it, one thread per face node (edges / corners counted once).
+// ----------------------------------------------------------------------------------------------
+struct FaceSet {
+  int nface;
+  int axis[6], fixed[6];          // fixed axis and its index (z: LOCAL plane)
+  int lo[6][2], cnt[6][2];        // the two varying axes (ascending axis order): start and count
+  long long start[7];             // prefix sums of the node counts
+};
+
+template <int NC, bool CHEBY>
+__global__ void __launch_bounds__(128)
+k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, const __grid_constant__ FaceSet fs,
+            const double* __restrict__ coef, const double* __restrict__ dinv, const double* __restrict__ load,
+            const __grid_constant__ StencilDev a, ReduceBuf red, double* red_out) {
+  double acc_xy = 0.0, acc_yy = 0.0;
+  const long long total = fs.start[fs.nface];
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int f = 0;
+    while (f + 1 < fs.nface && t >= fs.start[f + 1]) ++f;
+    const long long r = t - fs.start[f];
+    const int u = fs.lo[f][0] + (int)(r % fs.cnt[f][0]);
+    const int v = fs.lo[f][1] + (int)(r / fs.cnt[f][0]);
+    int ix, iy, lz;
+    if (fs.axis[f] == 0) { ix = fs.fixed[f]; iy = u; lz = v; }
+    else if (fs.axis[f] == 1) { ix = u; iy = fs.fixed[f]; lz = v; }
+    else { ix = u; iy = v; lz = fs.fixed[f]; }
+    const int gz = lz + g.z0;
+    double bcv;
+    if (bc_node(g, bc, ix, iy, gz, &bcv)) continue;  // Dirichlet rows were written (masked) by the main kernel
+    const int cls = node_class(g, ix, iy, gz);
+    const long long idx = (long long)g.PX * iy + g.plane * lz + ix;
+    double acc[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) acc[i] = 0.0;
+    for (int k = 0; k < g.nk; ++k) {
+      const double* cf = coef + ((size_t)cls * PDE_NOFF + g.kidx[k]) * (NC * NC);
+      const long long off = g.koff[k];
+      double xv[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) xv[j] = a.x[idx + off + j * g.comp_stride];
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[i] = fma(__ldg(cf + i * NC + j), xv[j], acc[i]);
+    }
+    const double ld = a.b ? 0.0 : __ldg(load + cls);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const long long ii = idx + i * g.comp_stride;
+      const double B = a.b ? a.b[ii] : a.bconst[i] * ld;
+      if (CHEBY) {
+        const double dn = a.c1 * a.d[ii] + a.c2 * __ldg(dinv + cls * NC + i) * (B - acc[i]);
+        const double yv = a.x[ii] + dn;
+        a.d[ii] = dn;
+        a.y[ii] = yv;
+        acc_xy = fma(B, yv, acc_xy);
+      } else {
+        const double yv = a.bscale * B + a.ascale * acc[i];
+        if (a.y) a.y[ii] = yv;
+        acc_xy = fma(a.x[ii], yv, acc_xy);
+        acc_yy = fma(yv, yv, acc_yy);
+      }
+    }
+  }
+  if (a.do_reduce) {
+    if (CHEBY) {
+      double v[1] = {acc_xy};
+      block_reduce_finalize<1, true>(v, red, red_out);
+    } else {
+      double v[2] = {acc_xy, acc_yy};
+      block_reduce_finalize<2, true>(v, red, red_out);
+    }
+  }
+}
+
+int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
+  if (a.cheby == 2) PDE_FAIL("fused first sweeps need a uniform diagonal (no natural faces)");
+  FaceSet fs;
+  memset(&fs, 0, sizeof(fs));
+  const int n0 = g.nn[0], n1 = g.nn[1];
+  auto add = [&](int axis, int fixed, int lo0, int c0, int lo1, int c1) {
+    if (c0 <= 0 || c1 <= 0) return;
+    const int f = fs.nface++;
+    fs.axis[f] = axis; fs.fixed[f] = fixed;
+    fs.lo[f][0] = lo0; fs.cnt[f][0] = c0; fs.lo[f][1] = lo1; fs.cnt[f][1] = c1;
+    fs.start[f + 1] = fs.start[f] + (long long)c0 * c1;
+  };
+  // a face whose Dirichlet flag is set contributes no free rows, except that the reference's "other_faces"
+  // rule (side_excl) leaves the x-end columns of side faces free: keep such faces listed
+  const bool keep_all = bc.side_excl != 0;
+  if (g.nc[0] > 0) {
+    if (!bc.on[0] || keep_all) add(0, 0, 0, n1, 0, g.nzl);
+    if (!bc.on[1] || keep_all) add(0, n0 - 1, 0, n1, 0, g.nzl);
+  }
+  if (g.nc[1] > 0 && n0 > 2) {
+    if (!bc.on[2] || keep_all) add(1, 0, 1, n0 - 2, 0, g.nzl);
+    if (!bc.on[3] || keep_all) add(1, n1 - 1, 1, n0 - 2, 0, g.nzl);
+  }
+  if (g.nc[2] > 0 && n0 > 2 && (n1 > 2 || g.nc[1] == 0)) {
+    const int ylo = g.nc[1] > 0 ? 1 : 0, ycnt = g.nc[1] > 0 ? n1 - 2 : 1;
+    if (g.z0 == 0 && (!bc.on[4] || keep_all)) add(2, 0, 1, n0 - 2, ylo, ycnt);
+    if (g.z0 + g.nzl == g.nzg && (!bc.on[5] || keep_all)) add(2, g.nzl - 1, 1, n0 - 2, ylo, ycnt);
+  }
+  const long long total = fs.start[fs.nface];
+  if (total == 0) return 0;
+  StencilDev sd;
+  sd.x = a.x; sd.b = a.b; sd.y = a.y; sd.d = a.d;
+  for (int i = 0; i < 3; ++i) sd.bconst[i] = a.bconst[i];
+  sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2; sd.s0 = a.s0;
+  sd.do_reduce = a.reduce_slot_xy >= 0;
+  sd.first2 = 0;
+  int blocks = flat_blocks(c, total, 128);
+  double* out = sd.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
+  if (a.cheby) {
+    DISPATCH_NC(op.ncomp, (k_face_rows<NC, true><<<blocks, 128, 0, c->stream>>>(g, bc, fs, op.coef, op.dinv, op.load, sd,
+                                                                               c->red, out)));
+  } else {
+    DISPATCH_NC(op.ncomp, (k_face_rows<NC, false><<<blocks, 128, 0, c->stream>>>(g, bc, fs, op.coef, op.dinv, op.load,
+                                                                                sd, c->red, out)));
+  }
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, double* r, const double* p,
                      const double* q, int slot_rho, int slot_pap, int slot_rho_new, int slot_rr, int jacobi) {

@@ -12,8 +12,8 @@
 //   to the three outputs q-1, q, q+1 it keeps in registers, then retires output q-1.  A thread owns a
 //   strip of YS nodes along y, which cuts shared-memory reads to (3*YS+4)/YS values per output.
 //   Algorithmic HBM traffic: read x once, write y once (16 B/dof; Chebyshev sweep 40 B/dof).
-//   Nodes whose element patch is incomplete (natural / traction-free faces) are recomputed from the
-//   27-class table when they retire; Dirichlet rows are masked.
+//   Nodes whose element patch is incomplete (natural / traction-free faces) are skipped here and computed
+//   by k_face_rows (kernels.cu) from the 27-class table right after; Dirichlet rows are masked.
 #include <cuda.h>
 
 #include <cmath>
@@ -153,32 +153,6 @@ __device__ __forceinline__ void plane_contrib(const Coef<NC>& C, const double (&
   }
 }
 
-// Row of a node whose element patch is incomplete (natural / traction-free faces): recomputed from the
-// 27-class table with global loads.  Rare (domain faces only), kept out of line to protect registers.
-template <int NC>
-struct RowVal {
-  double v[NC];
-};
-template <int NC>
-__device__ __noinline__ RowVal<NC> slow_row(const Grid& g, const double* __restrict__ coef, const double* __restrict__ x,
-                                            long long idx, int cls) {
-  RowVal<NC> r;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) r.v[c] = 0.0;
-  for (int k = 0; k < PDE_NOFF; ++k) {
-    const double* cf = coef + ((size_t)cls * PDE_NOFF + k) * (NC * NC);
-    const long long off = g.koff[k];
-    double xv[NC];
-#pragma unroll
-    for (int q = 0; q < NC; ++q) xv[q] = x[idx + off + q * g.comp_stride];
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-#pragma unroll
-      for (int q = 0; q < NC; ++q) r.v[c] = fma(__ldg(cf + c * NC + q), xv[q], r.v[c]);
-  }
-  return r;
-}
-
 // MODE: 0 apply (B = bconst*load), 1 residual-type (B from field b), 2 Chebyshev sweep, 3 fused first TWO
 // Chebyshev sweeps from a zero guess (input field = right-hand side; needs a uniform Jacobi diagonal)
 enum { M_APPLY = 0, M_RESID = 1, M_CHEBY = 2, M_FIRST2 = 3 };
@@ -186,8 +160,7 @@ enum { M_APPLY = 0, M_RESID = 1, M_CHEBY = 2, M_FIRST2 = 3 };
 template <int NC, int YS, int MODE, bool SPEC>
 __global__ void __launch_bounds__(NC == 1 ? 384 : 256)
 k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
-          const __grid_constant__ Coef<NC> C, const double* __restrict__ coef, const double* __restrict__ dinv,
-          const double* __restrict__ load, const __grid_constant__ SweepArgs a, const __grid_constant__ SweepGeom sw,
+          const __grid_constant__ Coef<NC> C, const __grid_constant__ SweepArgs a, const __grid_constant__ SweepGeom sw,
           ReduceBuf red, double* red_out) {
   constexpr bool CHEBY = MODE >= M_CHEBY;
   constexpr bool HAS_B = MODE == M_RESID || MODE == M_CHEBY;
@@ -263,7 +236,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
 
   // per-thread node flags, constant over the z march: bit j describes node (ix, iy0+j).
   //   mrow[j] = 0 for Dirichlet / out-of-range nodes, 1 for free nodes: masked rows need no branch.
-  unsigned valid = 0, slowxy = 0;
+  unsigned valid = 0, slowxy = 0, freexy = 0;  // freexy: valid and not Dirichlet through an x/y face
   double mrow[YS];
   bool z_excl = false;  // "other_faces" predicate: side faces skip the x-end columns
 #pragma unroll
@@ -280,6 +253,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
       bool d = (xe0 && bc.on[0]) || (xe1 && bc.on[1]);
       if (!d && !z_excl) d = (ye0 && bc.on[2]) || (ye1 && bc.on[3]);
       mrow[j] = d ? 0.0 : 1.0;
+      if (!d) freexy |= 1u << j;
       if (!d && (xe0 || xe1 || ye0 || ye1)) slowxy |= 1u << j;
     }
   }
@@ -366,39 +340,12 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
       const bool zdir = !z_excl && ((ze0 && bc.on[4]) || (ze1 && bc.on[5]));
       const double mz = zdir ? 0.0 : 1.0;
       unsigned todo = valid;
-      const unsigned slow = zdir ? 0u : ((ze0 || ze1) ? valid : slowxy);
+      const unsigned slow = zdir ? 0u : ((ze0 || ze1) ? freexy : slowxy);
       // plane base pointers are uniform over the CTA; per-thread offsets fit 32 bits
       const long long pbase = (long long)g.plane * zout;
-      if (slow) {  // incomplete element patches (domain faces only): class-table rows, emitted here
-#pragma unroll
-        for (int j = 0; j < YS; ++j) {
-          if (!((slow >> j) & 1u) || mrow[j] == 0.0) continue;
-          todo &= ~(1u << j);
-          const int cls = node_class(g, ix, iy0 + j, gz);
-          const long long idx = pbase + col0 + (long long)g.PX * j;
-          const RowVal<NC> rv = slow_row<NC>(g, coef, a.x, idx, cls);
-          const double ld = __ldg(load + cls);
-#pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const long long ii = idx + c * g.comp_stride;
-            const double B = HAS_B ? bv[j][c] : a.bconst[c] * ld;
-            if (CHEBY) {
-              // (M_FIRST2 never reaches here: it requires all faces Dirichlet, so no slow rows exist)
-              const double dn = a.c1 * dv[j][c] + a.c2 * __ldg(dinv + cls * NC + c) * (B - rv.v[c]);
-              a.d[ii] = dn;
-              const double yv = xv[j][c] + dn;
-              a.y[ii] = yv;
-              red_xy = fma(B, yv, red_xy);
-            } else {
-              const double yv = a.bscale * B + a.ascale * rv.v[c];
-              if (a.y) a.y[ii] = yv;
-              red_xy = fma(xv[j][c], yv, red_xy);
-              red_yy = fma(yv, yv, red_yy);
-            }
-          }
-        }
-      }
-      // interior-class rows: Dirichlet / out-of-range / already emitted rows are masked by m = 0
+      // rows on natural faces (incomplete element patches) are left to k_face_rows, launched right after
+      todo &= ~slow;
+      // interior-class rows: Dirichlet / out-of-range / face rows are masked by m = 0
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const double* __restrict__ dcp = CHEBY ? a.d + pbase + c * g.comp_stride : nullptr;
@@ -587,9 +534,11 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   for (int i = 0; i < 3; ++i) sa.dinv_int[i] = i < NC ? op.h_dinv_int[i] : 0.0;
   sa.do_reduce = a.reduce_slot_xy >= 0;
   double* out = sa.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
-  kern<<<(unsigned)items, nt + (sw.spec ? 32 : 0), smem, c->stream>>>(tm, g, bc, C, op.coef, op.dinv, op.load, sa, sw, c->red, out);
+  kern<<<(unsigned)items, nt + (sw.spec ? 32 : 0), smem, c->stream>>>(tm, g, bc, C, sa, sw, c->red, out);
   c->launches++;
   CUDA_OK(cudaGetLastError());
+  // natural (non-Dirichlet) faces: their rows have incomplete element patches and come from the class table
+  if (!op.uniform_diag) PDE_OK(launch_face_rows(c, g, bc, op, a));
   return 0;
 }
 
