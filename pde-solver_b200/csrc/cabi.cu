@@ -452,20 +452,6 @@ extern "C" int pde_op_apply(pde_ctx* c, const pde_op_params* p, const double* x,
   return d2h(c, y, dense.p, sizeof(double) * nloc * nc);
 }
 
-__global__ void k_fill_pattern(const __grid_constant__ Grid g, int ncomp, double* __restrict__ x) {
-  const long long rows = (long long)g.nn[1] * g.nzl;
-  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
-       row += (long long)gridDim.x * blockDim.y) {
-    const int iy = (int)(row % g.nn[1]);
-    const int lz = (int)(row / g.nn[1]);
-    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x)
-      for (int i = 0; i < ncomp; ++i) {
-        const long long node = row * g.nn[0] + ix;
-        x[(long long)g.PX * iy + g.plane * lz + ix + i * g.comp_stride] = sin(0.37 * (double)(node % 1000003) + i) + 0.5;
-      }
-  }
-}
-
 extern "C" int pde_op_bench(pde_ctx* c, const pde_op_params* p, int reps, int warmup, double* ms_per_apply,
                             int64_t* ndofs) {
   if (!c || !p) PDE_FAIL("null argument");
@@ -476,10 +462,7 @@ extern "C" int pde_op_bench(pde_ctx* c, const pde_op_params* p, int reps, int wa
   const Grid& g = G.A.g;
   PDE_OK(G.x.alloc(c, g, nc));
   PDE_OK(G.y.alloc(c, g, nc));
-  RowLaunch rl = row_launch(c, g);
-  k_fill_pattern<<<rl.grid, rl.block, 0, c->stream>>>(g, nc, G.x.p);
-  c->launches++;
-  CUDA_OK(cudaGetLastError());
+  PDE_OK(launch_fill_pattern(c, g, G.A.bc, nc, G.x.p));
   StencilArgs a;
   a.x = G.x.p; a.y = G.y.p; a.variant = p->variant; a.reduce_slot_xy = S_XY;
   for (int i = 0; i < warmup; ++i) PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
@@ -499,17 +482,33 @@ static int solve_with(pde_ctx* c, OpGuard& G, const pde_op_params* p, const pde_
   const int nc = G.A.tab.ncomp;
   long long ndofs = (long long)G.A.g.nn[0] * G.A.g.nn[1] * G.A.g.nzg * nc;
   bool use_mg = false;
-  if (o.precond != PDE_PRECOND_JACOBI) {
-    double p0 = p->kind == PDE_OP_ELASTICITY ? p->lam : (p->kind == PDE_OP_MASS ? 1.0 : (p->kind == PDE_OP_STIFFNESS ? 0.0 : p->alpha));
-    double p1 = p->kind == PDE_OP_ELASTICITY ? p->mu : (p->kind == PDE_OP_MASS ? 0.0 : (p->kind == PDE_OP_STIFFNESS ? 1.0 : p->beta));
-    PDE_OK(G.mg.build(c, G.A, p->kind == PDE_OP_ELASTICITY ? PDE_OP_ELASTICITY : PDE_OP_HEAT, p0, p1));
-    G.mg.nu = o.cheby_degree > 0 ? o.cheby_degree : 2;
-    G.mg.ratio = o.cheby_ratio > 1 ? o.cheby_ratio : 8.0;
-    if (const char* e = getenv("PDE_B200_CHEBY_DEGREE")) G.mg.nu = atoi(e) > 0 ? atoi(e) : G.mg.nu;
-    if (const char* e = getenv("PDE_B200_CHEBY_RATIO")) G.mg.ratio = atof(e) > 1 ? atof(e) : G.mg.ratio;
-    use_mg = choose_precond(o, c, ndofs, G.mg) == PDE_PRECOND_GMG;
-  }
-  PDE_OK(G.w.alloc(c, G.A.g, nc));
+  // hierarchy / work-vector setup is timed separately (st->setup_ms); callers subtract it from their region
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  CUDA_OK(cudaEventRecord(e0, c->stream));
+  int rc = 0;
+  do {
+    if (o.precond != PDE_PRECOND_JACOBI) {
+      double p0 = p->kind == PDE_OP_ELASTICITY ? p->lam : (p->kind == PDE_OP_MASS ? 1.0 : (p->kind == PDE_OP_STIFFNESS ? 0.0 : p->alpha));
+      double p1 = p->kind == PDE_OP_ELASTICITY ? p->mu : (p->kind == PDE_OP_MASS ? 0.0 : (p->kind == PDE_OP_STIFFNESS ? 1.0 : p->beta));
+      if ((rc = G.mg.build(c, G.A, p->kind == PDE_OP_ELASTICITY ? PDE_OP_ELASTICITY : PDE_OP_HEAT, p0, p1))) break;
+      G.mg.nu = o.cheby_degree > 0 ? o.cheby_degree : 2;
+      G.mg.ratio = o.cheby_ratio > 1 ? o.cheby_ratio : 8.0;
+      if (const char* e = getenv("PDE_B200_CHEBY_DEGREE")) G.mg.nu = atoi(e) > 0 ? atoi(e) : G.mg.nu;
+      if (const char* e = getenv("PDE_B200_CHEBY_RATIO")) G.mg.ratio = atof(e) > 1 ? atof(e) : G.mg.ratio;
+      use_mg = choose_precond(o, c, ndofs, G.mg) == PDE_PRECOND_GMG;
+    }
+    if ((rc = G.w.alloc(c, G.A.g, nc))) break;
+  } while (0);
+  cudaEventRecord(e1, c->stream);
+  cudaEventSynchronize(e1);
+  float sms = 0;
+  cudaEventElapsedTime(&sms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc) return rc;
+  st->setup_ms += sms;
   return pcg_solve(c, G.A, use_mg ? &G.mg : nullptr, G.w, x, r, bn2, o, st);
 }
 
@@ -556,7 +555,7 @@ extern "C" int pde_op_solve(pde_ctx* c, const pde_op_params* p, const pde_solver
   CUDA_OK(cudaEventSynchronize(c->ev1));
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  st.solve_ms = ms;
+  st.solve_ms = ms - st.setup_ms;
   st.launches = c->launches - l0;
   PDE_OK(launch_pack(c, g, nc, G.x.p, (double*)dense.p, 0));
   PDE_OK(d2h(c, x, dense.p, sizeof(double) * nloc * nc));
@@ -615,7 +614,7 @@ extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const
   CUDA_OK(cudaEventSynchronize(c->ev1));
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  st.solve_ms = ms;
+  st.solve_ms = ms - st.setup_ms;
   st.launches = c->launches - l0;
   // projected scalar: M v = sum_cells value_c |c|/(d+1)   (project(eq_expr, Vs), :1541-1546, 1714, 1862)
   SimplexGeom sg;
@@ -646,7 +645,7 @@ extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const
   CUDA_OK(cudaEventRecord(c->ev1, c->stream));
   CUDA_OK(cudaEventSynchronize(c->ev1));
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-  sp.solve_ms = ms;
+  sp.solve_ms = ms - sp.setup_ms;
   sp.launches = c->launches - l1;
   DevMem dense;
   PDE_OK(dense.alloc(sizeof(double) * nloc * nc));
