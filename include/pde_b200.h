@@ -48,6 +48,12 @@ int pde_host_free(void* p);
 int pde_nccl_unique_id(const char* libnccl_path, void* id128 /* 128 bytes out */);
 int pde_comm_init(pde_ctx* ctx, int rank, int world, const void* id128, const char* libnccl_path);
 
+/* host-only: the slab of vertex planes rank `rank` of `world` owns on multigrid level `level` (0 = the
+ * mesh itself, each level halves every axis).  Planes are indexed along the slowest axis of the natural
+ * numbering; rank r owns [z0, z0+nzl) of nzg planes.  Returns non-zero if the level does not exist. */
+int pde_slab_partition(int dim, const int32_t n[3], int rank, int world, int level, int32_t* z0, int32_t* nzl,
+                       int32_t* nzg);
+
 /* ---- meshes, dof maps, boundary sets (bit-exact rows a2-a4 of SURVEY §8) ------------- */
 /* IntervalMesh :229,1516 / RectangleMesh :369,1648 / BoxMesh :533,1803.
  * dim in {1,2,3}; n[k] cells along axis k; domain [0,L[k]].  Generated on the GPU. */

@@ -83,7 +83,7 @@ def lib():
                      "pde_mesh_cells", "pde_dofmap_cells", "pde_boundary_mask", "pde_heat_solve",
                      "pde_heat_open", "pde_heat_set_state", "pde_heat_step", "pde_heat_get_state",
                      "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench",
-                     "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free"):
+                     "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -201,6 +201,14 @@ def mesh_counts(dim, n):
     nv, nc = C.c_int64(), C.c_int64()
     check(lib().pde_mesh_counts(int(dim), i3(n), C.byref(nv), C.byref(nc)))
     return nv.value, nc.value
+
+
+def slab_partition(dim, n, rank, world, level=0):
+    """(z0, nzl, nzg): vertex planes [z0, z0+nzl) of nzg that `rank` owns on multigrid `level` (host only)."""
+    z0, nzl, nzg = C.c_int32(), C.c_int32(), C.c_int32()
+    check(lib().pde_slab_partition(int(dim), i3(n), int(rank), int(world), int(level), C.byref(z0), C.byref(nzl),
+                                   C.byref(nzg)))
+    return z0.value, nzl.value, nzg.value
 
 
 def op_params(kind, dim, n, L, alpha=1.0, beta=1.0, lam=0.0, mu=0.0, bc=None, variant=0):

@@ -281,3 +281,25 @@ extern "C" int pde_op_table(const pde_op_params* p, double* table, int32_t* ncom
   if (table) std::memcpy(table, t.coef.data(), t.coef.size() * sizeof(double));
   return 0;
 }
+
+extern "C" int pde_slab_partition(int dim, const int32_t n_in[3], int rank, int world, int level, int32_t* z0,
+                                  int32_t* nzl, int32_t* nzg) {
+  if (dim < 1 || dim > 3) PDE_FAIL("dim must be 1, 2 or 3");
+  if (world < 1 || rank < 0 || rank >= world) PDE_FAIL("bad rank/world");
+  int32_t n[3] = {0, 0, 0};
+  for (int k = 0; k < dim; ++k) n[k] = n_in[k];
+  for (int l = 0; l < level; ++l) {
+    for (int k = 0; k < dim; ++k) {
+      if (n[k] % 2 != 0 || n[k] < 2) PDE_FAIL("level does not exist: an axis cannot be halved");
+      n[k] /= 2;
+    }
+    if (world > 1 && (n[dim - 1] * 2) % (2 * world) != 0) PDE_FAIL("level does not exist: coarse slabs would not nest");
+  }
+  const double L1[3] = {1, 1, 1};
+  Grid g;
+  PDE_OK(make_grid(dim, n, L1, rank, world, &g));
+  if (z0) *z0 = g.z0;
+  if (nzl) *nzl = g.nzl;
+  if (nzg) *nzg = g.nzg;
+  return 0;
+}

@@ -1,0 +1,114 @@
+"""N>1 host-side logic on CPU: slab partition arithmetic (C ABI, host only) and the torchrun plumbing of
+bench.py, exercised with world_size-2 gloo process groups (no GPU needed)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("dim,n,world", [(3, [512, 512, 4096], 8), (3, [1280, 256, 256], 8), (3, [64, 64, 64], 2),
+                                         (2, [4096, 4096], 4), (3, [16, 16, 33], 2)])
+def test_slab_partition_tiles_and_nests(dim, n, world):
+    from pde_solver_b200 import _lib
+    level = 0
+    while True:
+        try:
+            parts = [_lib.slab_partition(dim, n, r, world, level) for r in range(world)]
+        except _lib.PdeError:
+            assert level > 0          # level 0 always exists
+            break
+        nzg = parts[0][2]
+        assert nzg == n[dim - 1] // 2 ** level + 1
+        # disjoint cover of [0, nzg), rank order = plane order, every rank owns at least one plane
+        z = 0
+        for z0, nzl, g in parts:
+            assert z0 == z and nzl >= 1 and g == nzg
+            z += nzl
+        assert z == nzg
+        if level > 0:
+            # nesting: rank r's coarse slab starts at half of its fine start, so restriction of owned fine planes
+            # (plus one ghost plane) lands on owned coarse planes
+            for (z0c, nzlc, _), (z0f, nzlf, _) in zip(parts, prev):
+                assert 2 * z0c == z0f and 2 * (z0c + nzlc - 1) <= z0f + nzlf
+        prev = parts
+        level += 1
+    assert level >= 1
+
+
+def test_slab_partition_rejects_bad_arguments():
+    from pde_solver_b200 import _lib
+    with pytest.raises(_lib.PdeError):
+        _lib.slab_partition(3, [8, 8, 4], 0, 8)        # fewer cell layers than ranks
+    with pytest.raises(_lib.PdeError):
+        _lib.slab_partition(3, [8, 8, 8], 2, 2)        # rank out of range
+    with pytest.raises(_lib.PdeError):
+        _lib.slab_partition(1, [100], 0, 4)            # 1-D rods are never slab-partitioned
+
+
+WORKER = r"""
+import os, sys, json
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["REPO_ROOT"])
+from pde_solver_b200 import _lib
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = [6, 5, 8]
+z0, nzl, nzg = _lib.slab_partition(3, n, rank, world)
+plane = (n[0] + 1) * (n[1] + 1)
+glob = np.arange(plane * nzg, dtype=np.float64)                 # a global nodal field, natural order
+mine = glob[z0 * plane:(z0 + nzl) * plane].copy()
+# halo exchange as the library does it (first/last owned plane to the z-neighbours), here over gloo
+import torch
+lo = torch.zeros(plane, dtype=torch.float64); hi = torch.zeros(plane, dtype=torch.float64)
+reqs = []
+if rank > 0:
+    reqs += [dist.isend(torch.from_numpy(mine[:plane].copy()), rank - 1), dist.irecv(lo, rank - 1)]
+if rank < world - 1:
+    reqs += [dist.isend(torch.from_numpy(mine[-plane:].copy()), rank + 1), dist.irecv(hi, rank + 1)]
+for r in reqs: r.wait()
+ok = True
+if rank > 0: ok = ok and np.array_equal(lo.numpy(), glob[(z0 - 1) * plane:z0 * plane])
+if rank < world - 1: ok = ok and np.array_equal(hi.numpy(), glob[(z0 + nzl) * plane:(z0 + nzl + 1) * plane])
+# gather the slabs in rank order: must reproduce the global field (what bench.py / mgpu_check.py rely on)
+parts = [None] * world
+dist.all_gather_object(parts, mine)
+ok = ok and np.array_equal(np.concatenate(parts), glob)
+flags = [None] * world
+dist.all_gather_object(flags, bool(ok))
+if rank == 0: print(json.dumps({"ok": all(flags), "world": world}))
+dist.destroy_process_group()
+"""
+
+
+def _torchrun(args, env_extra=None, timeout=300):
+    env = dict(os.environ, REPO_ROOT=ROOT, OMP_NUM_THREADS="1")
+    env.update(env_extra or {})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300)] + args
+    return subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout,
+                          cwd=ROOT)
+
+
+def test_gloo_world2_slabs_and_halos(tmp_path):
+    w = tmp_path / "worker.py"
+    w.write_text(WORKER)
+    r = _torchrun([str(w)])
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line) == {"ok": True, "world": 2}
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    r = _torchrun(["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                      # rank 0 alone runs and prints
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
