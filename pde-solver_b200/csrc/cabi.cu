@@ -207,9 +207,6 @@ extern "C" int pde_heat_open(pde_ctx* c, const pde_heat_params* p, const pde_sol
   if (!p->steady && !(p->dt > 0)) PDE_FAIL("dt must be > 0");
   if (!(p->diffusivity > 0)) PDE_FAIL("diffusivity must be > 0");
   if (p->num_steps < 0) PDE_FAIL("num_steps must be >= 0");
-  if (p->initial_type == PDE_IC_COSINE || p->initial_type == PDE_IC_SINE)
-    PDE_FAIL("initial_type cosine/sine (consistent-mass projection of a P2-interpolated expression) "
-             "is not implemented in the CUDA path yet");
   pde_heat_state* s = new (std::nothrow) pde_heat_state();
   if (!s) PDE_FAIL("out of host memory");
   s->c = c;
@@ -253,7 +250,43 @@ extern "C" int pde_heat_open(pde_ctx* c, const pde_heat_params* p, const pde_sol
     // initial condition (reference :276-297, 408-426, 672-691): fill, then bc.apply(u_n.vector())
     double v0 = p->initial_type == PDE_IC_ZERO ? 0.0 : p->T_initial;
     if (p->steady) v0 = 0.0;
-    if ((rc = launch_fill_ic(c, s->g, s->bc, s->u.p, v0, 1))) break;
+    if (!p->steady && (p->initial_type == PDE_IC_COSINE || p->initial_type == PDE_IC_SINE)) {
+      // u_n = project(Expression(..., degree=2), V) (:276-290, 408-421, 672-685): consistent-mass solve of the
+      // P2-interpolated expression, then bc.apply(u_n.vector())
+      BcDev nobc;
+      std::memset(&nobc, 0, sizeof(nobc));
+      Operator Mf;
+      PcgWork pw;
+      int r2 = 0;
+      do {
+        if ((r2 = Mf.setup_scalar(c, s->g, nobc, 1.0, 0.0))) break;
+        SimplexGeom sg;
+        build_simplex_geom(p->dim, s->g.h, &sg);
+        if ((r2 = launch_p2_load(c, s->g, sg, p->initial_amplitude, p->initial_wavenumber,
+                                 p->initial_type == PDE_IC_SINE, p->n, p->L, s->r.p))) break;
+        if ((r2 = launch_zero(c, s->g, 1, s->u.p))) break;
+        if ((r2 = launch_dot(c, s->g, 1, s->r.p, s->r.p, S_TMP0))) break;
+        if (c->world > 1 && (r2 = comm_allreduce_scal(c, S_TMP0, 1))) break;
+        double bn2;
+        if ((r2 = read_scal(c, S_TMP0, 1, &bn2))) break;
+        if ((r2 = pw.alloc(c, s->g, 1))) break;
+        pde_solver_opts po = s->o;
+        po.precond = PDE_PRECOND_JACOBI;
+        po.rtol = 1e-13;
+        pde_stats pst;
+        std::memset(&pst, 0, sizeof(pst));
+        pst.converged = 1;
+        if ((r2 = pcg_solve(c, Mf, nullptr, pw, s->u.p, s->r.p, bn2, po, &pst))) break;
+        if (!pst.converged) { pde_set_error("initial-condition projection did not converge"); r2 = 1; break; }
+        if ((r2 = launch_apply_bc_values(c, s->g, s->bc, s->u.p))) break;
+      } while (0);
+      cudaStreamSynchronize(c->stream);
+      Mf.release();
+      pw.release();
+      if ((rc = r2)) break;
+    } else {
+      if ((rc = launch_fill_ic(c, s->g, s->bc, s->u.p, v0, 1))) break;
+    }
   } while (0);
   cudaEventRecord(e1, c->stream);
   cudaEventSynchronize(e1);

@@ -206,6 +206,9 @@ int launch_pack(pde_ctx* c, const Grid& g, int ncomp, const double* padded, doub
 int launch_unpack(pde_ctx* c, const Grid& g, int ncomp, const double* dense, double* padded, int interleave);
 int launch_cell_rhs(pde_ctx* c, const Grid& g, int ncomp, const SimplexGeom& sg, const double* u, double* rhs,
                     int mode, double lam, double mu, double Emod);
+// load vector of project(A*trig(k x)*trig(k y)*trig(k z) interpolated into P2, V)
+int launch_p2_load(pde_ctx* c, const Grid& g, const SimplexGeom& sg, double amp, double kw, int use_sin,
+                   const int32_t n_user[3], const double L_user[3], double* rhs);
 int launch_dense_solve(pde_ctx* c, int n, const double* Ainv, const long long* idx, const double* b, double* x);
 // multi-rank coarse solve: idx[j] < 0 marks dofs owned by another rank
 int launch_dense_gather(pde_ctx* c, int n, const long long* idx, const double* b, double* bglob);

@@ -865,6 +865,109 @@ int launch_cell_rhs(pde_ctx* c, const Grid& g, int ncomp, const SimplexGeom& sg,
 }
 
 // ----------------------------------------------------------------------------------------------
+// load vector of project(Expression("A*cos(k x)[*cos(k y)[*cos(k z)]]", degree=2), V)   (:276-290, 408-421,
+// 672-685): the expression is interpolated into P2 on every cell (values at vertices and edge midpoints)
+// and integrated exactly against the P1 basis.  The expression is separable, so its values come from one
+// table per axis sampled on the half-step lattice: tab[m] = trig(k * 0.5*(x[m/2] + x[(m+1)/2])).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_trig_table(int dim, int n, double Ls, int use_sin, double kw, int len, double* __restrict__ tab) {
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < len; m += gridDim.x * blockDim.x) {
+    const double ia = (double)(m / 2), ib = (double)((m + 1) / 2), dn = (double)n;
+    double xa, xb;
+    if (dim == 3) { xa = __ddiv_rn(__dmul_rn(ia, Ls), dn); xb = __ddiv_rn(__dmul_rn(ib, Ls), dn); }
+    else { xa = __dmul_rn(__ddiv_rn(Ls, dn), ia); xb = __dmul_rn(__ddiv_rn(Ls, dn), ib); }
+    const double x = 0.5 * (xa + xb);
+    tab[m] = use_sin ? sin(kw * x) : cos(kw * x);
+  }
+}
+
+struct P2Weights {
+  double vself, voth, ein, eout;
+};
+
+__global__ void __launch_bounds__(128)
+k_p2_load(const __grid_constant__ Grid g, const __grid_constant__ SimplexGeom sg, const __grid_constant__ P2Weights w,
+          double amp, const double* __restrict__ tx, const double* __restrict__ ty, const double* __restrict__ tz,
+          double* __restrict__ rhs) {
+  const long long rows = (long long)g.nn[1] * g.nzl;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int lz = (int)(row / g.nn[1]);
+    const int gz = lz + g.z0;
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      double acc = 0.0;
+      for (int o = 0; o < 8; ++o) {
+        const int ox = o & 1, oy = (o >> 1) & 1, oz = (o >> 2) & 1;
+        if ((ox && (g.nc[0] == 0 || ix == 0)) || (!ox && g.nc[0] > 0 && ix == g.nn[0] - 1)) continue;
+        if ((oy && (g.nc[1] == 0 || iy == 0)) || (!oy && g.nc[1] > 0 && iy == g.nn[1] - 1)) continue;
+        if ((oz && (g.nc[2] == 0 || gz == 0)) || (!oz && g.nc[2] > 0 && gz == g.nzg - 1)) continue;
+        const int cx = ix - ox, cy = iy - oy, cz = gz - oz;  // corner 0 of the cell
+        for (int t = 0; t < sg.nsimp; ++t) {
+          int li = -1;
+          for (int a = 0; a < sg.nv; ++a)
+            if (sg.corner[t][a] == o) li = a;
+          if (li < 0) continue;
+          // value at the point with doubled lattice index (mx,my,mz)
+          auto val = [&](int ca, int cb) {
+            const int mx = 2 * cx + (ca & 1) + (cb & 1);
+            const int my = 2 * cy + ((ca >> 1) & 1) + ((cb >> 1) & 1);
+            const int mz = 2 * cz + ((ca >> 2) & 1) + ((cb >> 2) & 1);
+            double v = amp * tx[mx];
+            if (g.nc[1] > 0) v *= ty[my];
+            if (g.nc[2] > 0) v *= tz[mz];
+            return v;
+          };
+          double s = 0.0;
+          for (int a = 0; a < sg.nv; ++a) s = fma(val(sg.corner[t][a], sg.corner[t][a]), a == li ? w.vself : w.voth, s);
+          for (int a = 0; a < sg.nv; ++a)
+            for (int b = a + 1; b < sg.nv; ++b)
+              s = fma(val(sg.corner[t][a], sg.corner[t][b]), (a == li || b == li) ? w.ein : w.eout, s);
+          acc = fma(s, sg.vol, acc);
+        }
+      }
+      rhs[(long long)g.PX * iy + g.plane * lz + ix] = acc;
+    }
+  }
+}
+
+int launch_p2_load(pde_ctx* c, const Grid& g, const SimplexGeom& sg, double amp, double kw, int use_sin,
+                   const int32_t n_user[3], const double L_user[3], double* rhs) {
+  // internal axis of user axis q: dim 2 maps user y -> internal z
+  const int dim = g.dim;
+  double* tabs[3] = {nullptr, nullptr, nullptr};
+  int rc = 0;
+  for (int q = 0; q < dim && !rc; ++q) {
+    const int iax = (dim == 2 && q == 1) ? 2 : q;
+    const int len = 2 * n_user[q] + 1;
+    if (cudaMalloc(&tabs[iax], sizeof(double) * len) != cudaSuccess) { pde_set_error("cudaMalloc failed (trig table)"); rc = 1; break; }
+    k_trig_table<<<(len + 255) / 256, 256, 0, c->stream>>>(dim, n_user[q], L_user[q], use_sin, kw, len, tabs[iax]);
+    c->launches++;
+  }
+  if (!rc) {
+    // int over the simplex of barycentric monomials: |c| d! prod(alpha!) / (d + |alpha|)!   (|c| applied in-kernel)
+    auto fac = [](int k) { double f = 1; for (int i = 2; i <= k; ++i) f *= i; return f; };
+    auto I = [&](int a, int b, int cc) { return fac(dim) * fac(a) * fac(b) * fac(cc) / fac(dim + a + b + cc); };
+    P2Weights w;
+    w.vself = 2 * I(3, 0, 0) - I(2, 0, 0);
+    w.voth = 2 * I(2, 1, 0) - I(1, 1, 0);
+    w.ein = 4 * I(2, 1, 0);
+    w.eout = dim >= 2 ? 4 * I(1, 1, 1) : 0.0;
+    RowLaunch rl = row_launch(c, g);
+    // absent axes point at the x table (never multiplied in)
+    k_p2_load<<<rl.grid, rl.block, 0, c->stream>>>(g, sg, w, amp, tabs[0], tabs[1] ? tabs[1] : tabs[0],
+                                                   tabs[2] ? tabs[2] : tabs[0], rhs);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) { pde_set_error("k_p2_load launch failed"); rc = 1; }
+  }
+  cudaStreamSynchronize(c->stream);
+  for (int q = 0; q < 3; ++q)
+    if (tabs[q]) cudaFree(tabs[q]);
+  return rc;
+}
+
+// ----------------------------------------------------------------------------------------------
 // mesh / dof-map / boundary-set generation (bit-exact integer + FP64 coordinate expressions)
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

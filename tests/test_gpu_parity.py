@@ -165,6 +165,19 @@ def test_heat_3d_directional_bcs_and_steady(P, precond):
     assert np.allclose(f.values[0], 20.0 * (1 - x / 2.0), atol=1e-9)   # known answer (i)
 
 
+@pytest.mark.parametrize("initial_type", ["cosine", "sine"])
+def test_heat_trig_initial_conditions(P, initial_type):
+    # project(Expression("A*cos(k*x[0])*...", degree=2), V), reference :276-290, 408-421, 672-685
+    ic = dict(initial_type=initial_type, initial_amplitude=3.0, initial_wavenumber=2.5)
+    okw = dict(diffusivity=1.0, T_initial=0.0, dt=0.01, num_steps=4, T_left=1.0, T_right=0.5, **ic)
+    _check_heat(P, 1, [2.0], [40], okw, dict(args=(2.0, 40, 1.0, 1.0, 0.5, 0.0, 0.01, 4), kw=ic), "jacobi")
+    okw = dict(diffusivity=0.7, T_initial=0.0, dt=0.02, num_steps=3, T_boundary=0.25, **ic)
+    _check_heat(P, 2, [1.0, 0.8], [20, 14], okw, dict(args=(1.0, 0.8, 20, 14, 0.7, 0.25, 0.0, 0.02, 3), kw=ic), "gmg")
+    okw = dict(diffusivity=1.0, T_initial=0.0, dt=0.01, num_steps=3, T_boundary=0.0, **ic)
+    _check_heat(P, 3, [1, 0.5, 0.75], [12, 6, 8], okw,
+                dict(args=(1, 0.5, 0.75, 12, 6, 8, 1.0, 0.0, 0.0, 0.01, 3), kw=ic), "gmg")
+
+
 # ---------------------------------------------------------------- elasticity vs oracle LU
 @pytest.mark.parametrize("precond", ["jacobi", "gmg"])
 @pytest.mark.parametrize("quantity", ["stress", "strain"])
