@@ -20,7 +20,8 @@ raise a clear error: they are outside this build's hot path (SURVEY.md §8f n3/n
 
 Solver knobs the reference does not have come from the environment so existing callers are
 unaffected: PDE_B200_RTOL (default 1e-10), PDE_B200_PRECOND (auto|gmg|jacobi),
-PDE_B200_SNAPSHOT_STRIDE (default 1 = every step, as the reference)."""
+PDE_B200_SNAPSHOT_STRIDE (default 1 = every step, as the reference), PDE_B200_STREAM (npz|xdmf: stream the
+snapshots to a file beside the pickle instead of holding them all in memory)."""
 import json
 import os
 import pickle
@@ -51,11 +52,25 @@ def _stride():
     return max(1, int(os.environ.get("PDE_B200_SNAPSHOT_STRIDE", "1")))
 
 
-def _save(field: TimeSeriesField, data_dir: str, stem: str) -> SolveResult:
+def _stream(data_dir: str, stem: str, dim: int, n, L):
+    """PDE_B200_STREAM=npz|xdmf: snapshots go to <data_dir>/<stem>_<uuid8>.<ext> one at a time (the pickle
+    then keeps only the first and last one).  Returns (writer or None, uuid8)."""
+    tag = uuid.uuid4().hex[:8]
+    fmt = os.environ.get("PDE_B200_STREAM", "").lower()
+    if fmt not in ("npz", "xdmf"):
+        return None, tag
+    from pde_solver_b200 import io as _io
+    Path(data_dir).mkdir(parents=True, exist_ok=True)
+    return _io.open_writer(fmt, str(Path(data_dir) / f"{stem}_{tag}.{fmt}"), dim, n, L, name="temperature"), tag
+
+
+def _save(field: TimeSeriesField, data_dir: str, stem: str, tag: Optional[str] = None, writer=None) -> SolveResult:
     """mkdir data_dir, pickle the field to <stem>_<uuid8>.pkl, return SolveResult (:1956-1974)."""
     data_path = Path(data_dir)
     data_path.mkdir(parents=True, exist_ok=True)
-    filepath = data_path / f"{stem}_{uuid.uuid4().hex[:8]}.pkl"
+    if writer is not None:
+        field.meta["snapshots_file"] = writer.close()
+    filepath = data_path / f"{stem}_{tag or uuid.uuid4().hex[:8]}.pkl"
     with open(filepath, "wb") as f:
         pickle.dump(field, f, protocol=pickle.HIGHEST_PROTOCOL)
     return SolveResult(data_file=str(filepath), dim=field.dim, meta=field.meta)
@@ -88,12 +103,13 @@ def solve_heat_1D(
 ) -> SolveResult:
     """1D heat equation u_t - k u_xx = f on (0, length), Dirichlet T_left / T_right, backward Euler
     (or steady when steady=True).  Returns the path of the pickled TimeSeriesField."""
+    writer, tag = _stream(data_dir, "heat_1d", 1, [nx], [length])
     field = _p._solve_heat_1d_raw(
         length=length, nx=nx, diffusivity=diffusivity, T_left=T_left, T_right=T_right, T_initial=T_initial,
         dt=dt, num_steps=num_steps, steady=steady, source_type=source_type, source_value=source_value,
         initial_type=initial_type, initial_amplitude=initial_amplitude, initial_wavenumber=initial_wavenumber,
-        snapshot_stride=_stride(), **_knobs())
-    return _save(field, data_dir, "heat_1d")
+        snapshot_stride=_stride(), stream_to=writer, **_knobs())
+    return _save(field, data_dir, "heat_1d", tag, writer)
 
 
 @mcp.tool()
@@ -116,12 +132,13 @@ def solve_heat_2D(
     initial_wavenumber: float = 1.0,
 ) -> SolveResult:
     """2D heat equation on [0,Lx]x[0,Ly] with the constant Dirichlet value T_boundary on the whole boundary."""
+    writer, tag = _stream(data_dir, "heat_2d", 2, [nx, ny], [Lx, Ly])
     field = _p._solve_heat_2d_raw(
         Lx=Lx, Ly=Ly, nx=nx, ny=ny, diffusivity=diffusivity, T_boundary=T_boundary, T_initial=T_initial, dt=dt,
         num_steps=num_steps, steady=steady, source_type=source_type, source_value=source_value,
         initial_type=initial_type, initial_amplitude=initial_amplitude, initial_wavenumber=initial_wavenumber,
-        snapshot_stride=_stride(), **_knobs())
-    return _save(field, data_dir, "heat_2d")
+        snapshot_stride=_stride(), stream_to=writer, **_knobs())
+    return _save(field, data_dir, "heat_2d", tag, writer)
 
 
 @mcp.tool()
@@ -154,14 +171,15 @@ def solve_heat_3D(
 ) -> SolveResult:
     """3D heat equation on the box [0,Lx]x[0,Ly]x[0,Lz]: uniform Dirichlet value T_boundary, or the
     directional values T_left (x=0) / T_right (x=Lx) / T_side (remaining faces)."""
+    writer, tag = _stream(data_dir, "heat_3d", 3, [nx, ny, nz], [Lx, Ly, Lz])
     field = _p._solve_heat_3d_raw(
         Lx=Lx, Ly=Ly, Lz=Lz, nx=nx, ny=ny, nz=nz, diffusivity=diffusivity, T_boundary=T_boundary,
         T_initial=T_initial, dt=dt, num_steps=num_steps, steady=steady, source_type=source_type,
         source_value=source_value, initial_type=initial_type, initial_amplitude=initial_amplitude,
         initial_wavenumber=initial_wavenumber, geometry_type=geometry_type, cylinder_radius=cylinder_radius,
         T_left=T_left, T_right=T_right, T_side=T_side, core_radius=core_radius,
-        core_diffusivity=core_diffusivity, snapshot_stride=_stride(), **_knobs())
-    return _save(field, data_dir, "heat_3d")
+        core_diffusivity=core_diffusivity, snapshot_stride=_stride(), stream_to=writer, **_knobs())
+    return _save(field, data_dir, "heat_3d", tag, writer)
 
 
 # ─────────────────────────────── elasticity (in scope) ───────────────────────────────

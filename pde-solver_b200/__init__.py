@@ -12,6 +12,7 @@ from .solvers import (  # noqa: F401
     last_stats,
 )
 from . import mesh  # noqa: F401
+from . import io  # noqa: F401
 
 __all__ = ["TimeSeriesField", "SolveResult", "PlotResult", "mesh", "last_stats",
            "_solve_heat_1d_raw", "_solve_heat_2d_raw", "_solve_heat_3d_raw",

@@ -43,7 +43,9 @@ def _finish(coords3, values, times, dim, meta, as_arrays):
 
 
 def _heat(dim, L, n, diffusivity, T_initial, dt, num_steps, steady, source_type, source_value, initial_type,
-          initial_amplitude, initial_wavenumber, bc, rtol, precond, snapshot_stride, u0=None, ctx=None):
+          initial_amplitude, initial_wavenumber, bc, rtol, precond, snapshot_stride, u0=None, ctx=None, stream_to=None):
+    """stream_to: an io.*SnapshotWriter.  Snapshots then go to the writer one at a time (device-resident
+    stepper, one pinned host buffer) and only the first and last are returned."""
     ctx = ctx or _lib.default_context()
     p = _lib.HeatParams()
     p.dim = dim
@@ -64,6 +66,8 @@ def _heat(dim, L, n, diffusivity, T_initial, dt, num_steps, steady, source_type,
     p.initial_wavenumber = float(initial_wavenumber)
     p.bc = bc
     nv, _ = _lib.mesh_counts(dim, n)
+    if stream_to is not None and not steady:
+        return _heat_streaming(ctx, p, dim, n, L, rtol, precond, u0, stream_to)
     nsnap = 1 if steady else 1 + int(num_steps) // max(1, int(snapshot_stride))
     values = np.empty((nsnap, nv), dtype=np.float64)
     times = np.empty(nsnap, dtype=np.float64)
@@ -78,17 +82,56 @@ def _heat(dim, L, n, diffusivity, T_initial, dt, num_steps, steady, source_type,
     return coords, values, times
 
 
+def _heat_streaming(ctx, p, dim, n, L, rtol, precond, u0, writer):
+    """Backward-Euler loop on the resident stepper (pde_heat_open/step/get_state): every kept snapshot is
+    copied to one pinned buffer and handed to the writer; host memory use is one snapshot."""
+    nv, _ = _lib.mesh_counts(dim, n)
+    st_h = C.c_void_p()
+    o = _lib.make_opts(rtol=rtol, precond=precond)
+    _lib.check(_lib.lib().pde_heat_open(ctx.handle, C.byref(p), C.byref(o), C.byref(st_h)))
+    buf = _lib.PinnedArray(nv)
+    acc = {"iters_total": 0, "solves": 0, "converged": 1, "solve_ms": 0.0, "launches": 0}
+    try:
+        if u0 is not None:
+            _lib.check(_lib.lib().pde_heat_set_state(st_h, _lib.ptr(np.ascontiguousarray(u0, dtype=np.float64))))
+        _lib.check(_lib.lib().pde_heat_get_state(st_h, _lib.ptr(buf.array)))
+        first = buf.array.copy()
+        writer.append(0.0, buf.array)
+        stride = max(1, int(p.snapshot_stride))
+        st = _lib.Stats()
+        times = [0.0]
+        for step in range(int(p.num_steps)):
+            _lib.check(_lib.lib().pde_heat_step(st_h, 1, C.byref(st)))
+            d = st.as_dict()
+            for k in ("iters_total", "solves", "solve_ms", "launches"):
+                acc[k] += d[k]
+            acc["converged"] &= d["converged"]
+            acc.update(ndofs=d["ndofs"], levels=d["levels"], final_relres=d["final_relres"], setup_ms=d["setup_ms"])
+            if (step + 1) % stride == 0:
+                _lib.check(_lib.lib().pde_heat_get_state(st_h, _lib.ptr(buf.array)))
+                times.append((step + 1) * p.dt)
+                writer.append(times[-1], buf.array)
+        last = buf.array.copy()
+    finally:
+        _lib.lib().pde_heat_close(st_h)
+        buf.free()
+    _last_stats.clear()
+    _last_stats.update(acc)
+    coords = mesh.coordinates(dim, n, L, ctx)
+    return coords, np.stack([first, last]), np.array([times[0], times[-1]])
+
+
 def _solve_heat_1d_raw(length: float, nx: int, diffusivity: float, T_left: float, T_right: float,
                        T_initial: float, dt: float, num_steps: int, steady: bool = False,
                        source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
                        initial_amplitude: float = 1.0, initial_wavenumber: float = 1.0, *, rtol: float = 1e-10,
                        precond: str = "auto", snapshot_stride: int = 1, as_arrays: Optional[bool] = None,
-                       u0=None) -> TimeSeriesField:
+                       u0=None, stream_to=None) -> TimeSeriesField:
     """1D heat equation on [0, length], Dirichlet T_left / T_right, backward Euler or steady."""
     bc = mesh.heat_bc(1, T_left=T_left, T_right=T_right)
     coords, values, times = _heat(1, [length], [nx], diffusivity, T_initial, dt, num_steps, steady, source_type,
                                   source_value, initial_type, initial_amplitude, initial_wavenumber, bc, rtol,
-                                  precond, snapshot_stride, u0)
+                                  precond, snapshot_stride, u0, stream_to=stream_to)
     # the reference sorts dofs by x (:252-254); natural order is already sorted
     order = np.argsort(coords[:, 0], kind="stable")
     meta = {"name": "temperature", "unit": "°C", "pde": "heat", "coordinate_system": "cartesian",
@@ -101,12 +144,12 @@ def _solve_heat_2d_raw(Lx: float, Ly: float, nx: int, ny: int, diffusivity: floa
                        source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
                        initial_amplitude: float = 1.0, initial_wavenumber: float = 1.0, *, rtol: float = 1e-10,
                        precond: str = "auto", snapshot_stride: int = 1, as_arrays: Optional[bool] = None,
-                       u0=None) -> TimeSeriesField:
+                       u0=None, stream_to=None) -> TimeSeriesField:
     """2D heat equation on [0,Lx]x[0,Ly], constant Dirichlet value on the whole boundary."""
     bc = mesh.heat_bc(2, T_boundary=T_boundary)
     coords, values, times = _heat(2, [Lx, Ly], [nx, ny], diffusivity, T_initial, dt, num_steps, steady,
                                   source_type, source_value, initial_type, initial_amplitude, initial_wavenumber,
-                                  bc, rtol, precond, snapshot_stride, u0)
+                                  bc, rtol, precond, snapshot_stride, u0, stream_to=stream_to)
     meta = {"name": "temperature", "unit": "°C", "pde": "heat", "coordinate_system": "cartesian", "Lx": Lx,
             "Ly": Ly, "source_type": source_type, "source_value": source_value, "steady": steady}
     return _finish(_embed3(coords, 2), values, times, 2, meta, as_arrays)
@@ -120,7 +163,8 @@ def _solve_heat_3d_raw(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: in
                        T_left: Optional[float] = None, T_right: Optional[float] = None,
                        T_side: Optional[float] = None, core_radius: Optional[float] = None,
                        core_diffusivity: Optional[float] = None, *, rtol: float = 1e-10, precond: str = "auto",
-                       snapshot_stride: int = 1, as_arrays: Optional[bool] = None, u0=None) -> TimeSeriesField:
+                       snapshot_stride: int = 1, as_arrays: Optional[bool] = None, u0=None,
+                       stream_to=None) -> TimeSeriesField:
     """3D heat equation on the box [0,Lx]x[0,Ly]x[0,Lz]; uniform or directional Dirichlet values."""
     if geometry_type == "cylinder" and cylinder_radius is not None:
         raise NotImplementedError(
@@ -132,7 +176,7 @@ def _solve_heat_3d_raw(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: in
     bc = mesh.heat_bc(3, T_boundary=T_boundary, T_left=T_left, T_right=T_right, T_side=T_side)
     coords, values, times = _heat(3, [Lx, Ly, Lz], [nx, ny, nz], diffusivity, T_initial, dt, num_steps, steady,
                                   source_type, source_value, initial_type, initial_amplitude, initial_wavenumber,
-                                  bc, rtol, precond, snapshot_stride, u0)
+                                  bc, rtol, precond, snapshot_stride, u0, stream_to=stream_to)
     use_directional_bc = (T_left is not None or T_right is not None or T_side is not None)
     meta = {"name": "temperature", "unit": "°C", "pde": "heat",
             "coordinate_system": "cartesian" if geometry_type == "box" else "cylindrical",

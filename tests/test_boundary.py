@@ -155,3 +155,43 @@ def test_stdio_round_trip(tmp_path):
     path = payload["data_file"] if os.path.isabs(payload["data_file"]) else os.path.join(str(tmp_path), payload["data_file"])
     field = pickle.load(open(path, "rb"))
     assert len(field.values) == 11 and len(field.values[0]) == 101 and field.meta["pde"] == "heat"
+
+
+def test_snapshot_writers_round_trip(tmp_path):
+    from pde_solver_b200 import io
+    n, L = [3, 2, 1], [1.0, 0.5, 0.25]
+    nv = 4 * 3 * 2
+    snaps = [np.arange(nv, dtype=float) + 100 * k for k in range(3)]
+    for fmt in ("npz", "xdmf"):
+        with io.open_writer(fmt, tmp_path / f"s.{fmt}", 3, n, L, name="temperature", meta={"pde": "heat"}) as w:
+            for k, v in enumerate(snaps):
+                w.append(0.1 * k, v)
+    t, v = io.read_npz_series(tmp_path / "s.npz")
+    assert np.allclose(t, [0, 0.1, 0.2]) and np.array_equal(v, np.stack(snaps))
+    t, v = io.read_xdmf_series(str(tmp_path / "s.xdmf"))
+    assert np.allclose(t, [0, 0.1, 0.2]) and np.array_equal(v, np.stack(snaps))
+    xml = open(tmp_path / "s.xdmf").read()
+    from xml.dom import minidom
+    minidom.parseString(xml)                                        # well-formed
+    assert 'Dimensions="2 3 4"' in xml and 'TopologyType="3DCoRectMesh"' in xml and 'Seek="192"' in xml
+    with pytest.raises(ValueError):
+        io.XdmfSnapshotWriter(tmp_path / "bad", 3, n, L).append(0.0, np.zeros(5))
+
+
+@pytest.mark.gpu
+def test_streaming_solve_matches_in_memory(server, tmp_path, monkeypatch):
+    import pde_solver_b200 as P
+    from pde_solver_b200 import io
+    full = P._solve_heat_3d_raw(1, 1, 1, 12, 10, 8, 1.0, 0.0, 20.0, 0.01, 6, as_arrays=True)
+    with io.open_writer("npz", tmp_path / "a.npz", 3, [12, 10, 8], [1, 1, 1]) as w:
+        part = P._solve_heat_3d_raw(1, 1, 1, 12, 10, 8, 1.0, 0.0, 20.0, 0.01, 6, as_arrays=True, stream_to=w,
+                                    snapshot_stride=2)
+    t, v = io.read_npz_series(tmp_path / "a.npz")
+    assert np.allclose(t, [0, 0.02, 0.04, 0.06])
+    assert np.array_equal(v, full.values[[0, 2, 4, 6]])            # same kernels, same arithmetic
+    assert np.array_equal(part.values, full.values[[0, 6]]) and np.allclose(part.times, [0, 0.06])
+    monkeypatch.setenv("PDE_B200_STREAM", "xdmf")
+    res = server.solve_heat_2D(nx=8, ny=8, num_steps=3, data_dir=str(tmp_path))
+    assert res.meta["snapshots_file"].endswith(".xdmf")
+    t, v = io.read_xdmf_series(res.meta["snapshots_file"])
+    assert v.shape == (4, 81)
