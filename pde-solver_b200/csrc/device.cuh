@@ -165,10 +165,12 @@ struct StencilArgs {
   const double* x = nullptr;   // input field (ghost/pad zero)
   const double* b = nullptr;   // optional right-hand side field; if null, B_i = bconst[c]*load[class]
   double* y = nullptr;         // output (may be null: reductions only)
-  double* d = nullptr;         // Chebyshev direction (cheby mode)
+  const double* xprev = nullptr;  // cheby: previous iterate x_{k-1} (may alias y); the direction is never stored,
+                                  // d_{k-1} = x_k - x_{k-1}
+  int prev_mode = 0;           // 0: restart (c1 = 0), 1: xprev pointer, 2: x_{k-1} = 0, 3: x_{k-1} = s0*dinv*b
   double bconst[3] = {0, 0, 0};
   double bscale = 0, ascale = 1;  // y = bscale*B + ascale*(A x)
-  double c1 = 0, c2 = 0;          // cheby: d = c1*d + c2*dinv*(B - A x); y = x + d
+  double c1 = 0, c2 = 0;          // cheby: d = c1*(x - xprev) + c2*dinv*(B - A x); y = x + d
   double s0 = 0;                  // cheby == 2: coefficient of the (implicit) first sweep, d1 = s0*dinv*b
   int cheby = 0;                  // 1: one sweep; 2: first TWO sweeps from a zero guess, x = right-hand side
                                   // reduce_slot_xy with cheby: receives sum B.y (one value)
@@ -191,9 +193,9 @@ int launch_copy(pde_ctx* c, const Grid& g, int ncomp, double* dst, const double*
 int launch_axpy(pde_ctx* c, const Grid& g, int ncomp, double* y, const double* x, double alpha);
 // e = u - uold ; uold = u ; u = u + e
 int launch_extrapolate(pde_ctx* c, const Grid& g, int ncomp, double* u, double* uold, double* e);
-// first Chebyshev sweep from a zero guess: d = s*dinv*b ; x = d
-int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* b, double* d,
-                       double* x, double s);
+// first Chebyshev sweep from a zero guess: x = s*dinv*b
+int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* b, double* x,
+                       double s);
 int launch_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcc, int ncomp, const double* rf,
                     double* bcoarse);
 int launch_prolong_add(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcf, int ncomp, const double* xc,

@@ -24,7 +24,8 @@ struct StencilDev {
   const double* x;
   const double* b;
   double* y;
-  double* d;
+  const double* xprev;
+  int prev_mode;
   double bconst[3];
   double bscale, ascale, c1, c2, s0;
   int do_reduce;
@@ -54,7 +55,6 @@ k_stencil(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
           if (CHEBY) {
-            a.d[idx + i * g.comp_stride] = 0.0;
             a.y[idx + i * g.comp_stride] = a.x[idx + i * g.comp_stride];
           } else if (a.y) {
             a.y[idx + i * g.comp_stride] = 0.0;
@@ -106,10 +106,12 @@ k_stencil(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
             yv = d1 + dn;
           } else {
             Bv = B;
-            dn = a.c1 * a.d[ii] + a.c2 * di * (B - acc[i]);
-            yv = a.x[ii] + dn;
+            const double xo = a.x[ii];
+            const double dprev = a.prev_mode == 1 ? xo - a.xprev[ii]
+                               : (a.prev_mode == 2 ? xo : (a.prev_mode == 3 ? xo - a.s0 * di * B : 0.0));
+            dn = a.c1 * dprev + a.c2 * di * (B - acc[i]);
+            yv = xo + dn;
           }
-          a.d[ii] = dn;
           a.y[ii] = yv;
           if (a.do_reduce) acc_xy = fma(Bv, yv, acc_xy);
         } else {
@@ -140,7 +142,7 @@ static int launch_stencil_t(pde_ctx* c, const Grid& g, const BcDev& bc, const Op
   for (int k = 0; k < PDE_NOFF; ++k)
     for (int q = 0; q < NC * NC; ++q) ic.c[k][q] = op.h_int[k * NC * NC + q];
   StencilDev sd;
-  sd.x = a.x; sd.b = a.b; sd.y = a.y; sd.d = a.d;
+  sd.x = a.x; sd.b = a.b; sd.y = a.y; sd.xprev = a.xprev; sd.prev_mode = a.prev_mode;
   for (int i = 0; i < 3; ++i) sd.bconst[i] = a.bconst[i];
   sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2; sd.s0 = a.s0;
   sd.first2 = a.cheby == 2;
@@ -295,9 +297,10 @@ k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, co
       const long long ii = idx + i * g.comp_stride;
       const double B = a.b ? a.b[ii] : a.bconst[i] * ld;
       if (CHEBY) {
-        const double dn = a.c1 * a.d[ii] + a.c2 * __ldg(dinv + cls * NC + i) * (B - acc[i]);
-        const double yv = a.x[ii] + dn;
-        a.d[ii] = dn;
+        const double xo = a.x[ii];
+        const double dprev = a.prev_mode == 1 ? xo - a.xprev[ii] : (a.prev_mode == 2 ? xo : 0.0);
+        const double dn = a.c1 * dprev + a.c2 * __ldg(dinv + cls * NC + i) * (B - acc[i]);
+        const double yv = xo + dn;
         a.y[ii] = yv;
         acc_xy = fma(B, yv, acc_xy);
       } else {
@@ -350,7 +353,7 @@ int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op
   const long long total = fs.start[fs.nface];
   if (total == 0) return 0;
   StencilDev sd;
-  sd.x = a.x; sd.b = a.b; sd.y = a.y; sd.d = a.d;
+  sd.x = a.x; sd.b = a.b; sd.y = a.y; sd.xprev = a.xprev; sd.prev_mode = a.prev_mode;
   for (int i = 0; i < 3; ++i) sd.bconst[i] = a.bconst[i];
   sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2; sd.s0 = a.s0;
   sd.do_reduce = a.reduce_slot_xy >= 0;
@@ -489,7 +492,7 @@ int launch_axpy(pde_ctx* c, const Grid& g, int ncomp, double* y, const double* x
 template <int NC>
 __global__ void __launch_bounds__(128)
 k_cheby_first(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, const double* __restrict__ dinv,
-              const double* __restrict__ b, double* __restrict__ d, double* __restrict__ x, double s) {
+              const double* b, double* x, double s) {
   const long long rows = (long long)g.nn[1] * g.nzl;
   for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
        row += (long long)gridDim.x * blockDim.y) {
@@ -504,18 +507,16 @@ k_cheby_first(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, 
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
         const long long ii = rbase + ix + i * g.comp_stride;
-        const double v = isdir ? 0.0 : s * __ldg(dinv + cls * NC + i) * b[ii];
-        d[ii] = v;
-        x[ii] = v;
+        x[ii] = isdir ? 0.0 : s * __ldg(dinv + cls * NC + i) * b[ii];
       }
     }
   }
 }
 
-int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* b, double* d,
-                       double* x, double s) {
+int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* b, double* x,
+                       double s) {
   RowLaunch rl = row_launch(c, g);
-  DISPATCH_NC(op.ncomp, (k_cheby_first<NC><<<rl.grid, rl.block, 0, c->stream>>>(g, bc, op.dinv, b, d, x, s)));
+  DISPATCH_NC(op.ncomp, (k_cheby_first<NC><<<rl.grid, rl.block, 0, c->stream>>>(g, bc, op.dinv, b, x, s)));
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -208,7 +208,6 @@ static int estimate_lmax(pde_ctx* c, MGLevel& L, int iters) {
   const int nc = L.op.dev.ncomp;
   double* x = L.xa.p;
   double* y = L.xb.p;
-  double* z = L.r.p;
   // deterministic start vector with all frequencies: x_i = sin(0.37 i) + 0.5 on free nodes
   PDE_OK(launch_fill_pattern(c, g, L.op.bc, nc, x));
   double lam = 0.0;
@@ -217,7 +216,7 @@ static int estimate_lmax(pde_ctx* c, MGLevel& L, int iters) {
     a.x = x; a.y = y; a.reduce_slot_xy = S_TMP0;
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, x));
     PDE_OK(launch_stencil(c, g, L.op.bc, L.op.dev, a));
-    PDE_OK(launch_cheby_first(c, g, L.op.bc, L.op.dev, y, z, y, 1.0));  // y <- D^-1 y
+    PDE_OK(launch_cheby_first(c, g, L.op.bc, L.op.dev, y, y, 1.0));  // y <- D^-1 y
     PDE_OK(launch_dot(c, g, nc, y, y, S_TMP0));
     PDE_OK(launch_dot(c, g, nc, x, x, S_TMP1));
     if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_TMP0, 2));
@@ -232,7 +231,6 @@ static int estimate_lmax(pde_ctx* c, MGLevel& L, int iters) {
   PDE_OK(launch_zero(c, g, nc, L.xa.p));
   PDE_OK(launch_zero(c, g, nc, L.xb.p));
   PDE_OK(launch_zero(c, g, nc, L.r.p));
-  PDE_OK(launch_zero(c, g, nc, L.d.p));
   if (lam > 0.0) {
     const double est = 1.1 * lam;
     if (est < L.op.dev.gershgorin) L.op.dev.gershgorin = est;
@@ -260,7 +258,6 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
     else PDE_OK(L->op.setup_scalar(c, g, fine.bc, p0, p1));
     PDE_OK(L->xa.alloc(c, g, ncomp));
     PDE_OK(L->xb.alloc(c, g, ncomp));
-    PDE_OK(L->d.alloc(c, g, ncomp));
     PDE_OK(L->r.alloc(c, g, ncomp));
     if (level > 0) PDE_OK(L->b.alloc(c, g, ncomp));
     lv.push_back(std::move(L));
@@ -303,7 +300,7 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
 void Hierarchy::release() {
   for (auto& L : lv) {
     L->op.release();
-    L->b.release(); L->xa.release(); L->xb.release(); L->r.release(); L->d.release();
+    L->b.release(); L->xa.release(); L->xb.release(); L->r.release();
     if (L->Ainv) cudaFree(L->Ainv);
     if (L->idx) cudaFree(L->idx);
     if (L->bglob) cudaFree(L->bglob);
@@ -312,8 +309,12 @@ void Hierarchy::release() {
 }
 
 struct Cheby {
-  double theta, delta, sigma, rho;
+  double theta, delta, sigma, rho, lmax_;
+  int kind = 1;  // 1: first-kind Chebyshev on [lmax/ratio, lmax]; 4: fourth-kind (Lottes), needs lmax only
   void init(double lmax, double ratio) {
+    static const int env_kind = getenv("PDE_B200_CHEBY_KIND") ? atoi(getenv("PDE_B200_CHEBY_KIND")) : 1;
+    kind = env_kind == 4 ? 4 : 1;
+    lmax_ = lmax;
     const double lmin = lmax / ratio;
     theta = 0.5 * (lmax + lmin);
     delta = 0.5 * (lmax - lmin);
@@ -322,6 +323,12 @@ struct Cheby {
   }
   // coefficients of sweep k (k = 0 restarts the recurrence): d = c1 d + c2 Dinv r
   void coef(int k, double* c1, double* c2) {
+    if (kind == 4) {
+      if (k == 0) { *c1 = 0.0; *c2 = 4.0 / (3.0 * lmax_); return; }
+      *c1 = (2.0 * k - 1.0) / (2.0 * k + 3.0);
+      *c2 = (8.0 * k + 4.0) / ((2.0 * k + 3.0) * lmax_);
+      return;
+    }
     if (k == 0) { rho = 1.0 / sigma; *c1 = 0.0; *c2 = 1.0 / theta; return; }
     const double rn = 1.0 / (2.0 * sigma - rho);
     *c1 = rn * rho;
@@ -337,35 +344,43 @@ static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double*
   Cheby ch;
   ch.init(L.op.dev.gershgorin, ratio);
   int k0 = 0;
+  int prev_mode = 0;   // how sweep k rebuilds d_{k-1} = x_k - x_{k-1}
+  double s0 = 0;
   if (dot_done) *dot_done = false;
   if (zero_guess && sweeps >= 2 && L.op.dev.uniform_diag) {
     // sweeps 0 and 1 in one pass over the data: x1 = s0 D^-1 b never touches memory
     StencilArgs a;
-    double c1, s0;
+    double c1;
     ch.coef(0, &c1, &s0);
     a.cheby = 2;
     a.s0 = s0;
     ch.coef(1, &a.c1, &a.c2);
-    a.x = b; a.y = *cur; a.d = L.d.p;
+    a.x = b; a.y = *cur;
     if (dot_slot >= 0 && sweeps == 2) { a.reduce_slot_xy = dot_slot; if (dot_done) *dot_done = true; }
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, const_cast<double*>(b)));
     PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
     k0 = 2;
+    prev_mode = 3;     // x_1 = s0 D^-1 b
   } else if (zero_guess) {
     double c1, c2;
     ch.coef(0, &c1, &c2);
-    PDE_OK(launch_cheby_first(c, L.op.g, L.op.bc, L.op.dev, b, L.d.p, *cur, c2));
+    PDE_OK(launch_cheby_first(c, L.op.g, L.op.bc, L.op.dev, b, *cur, c2));
     k0 = 1;
+    prev_mode = 2;     // x_0 = 0
   }
   for (int k = k0; k < sweeps; ++k) {
     StencilArgs a;
     a.cheby = 1;
-    a.x = *cur; a.y = *oth; a.b = b; a.d = L.d.p;
+    a.x = *cur; a.y = *oth; a.b = b;
     ch.coef(k, &a.c1, &a.c2);
+    a.prev_mode = k == 0 ? 0 : prev_mode;
+    a.s0 = s0;
+    a.xprev = a.prev_mode == 1 ? *oth : nullptr;   // the other buffer still holds x_{k-1}
     if (dot_slot >= 0 && k == sweeps - 1) { a.reduce_slot_xy = dot_slot; if (dot_done) *dot_done = true; }
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, *cur));
     PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
     std::swap(*cur, *oth);
+    prev_mode = 1;
   }
   return 0;
 }

@@ -25,7 +25,7 @@ struct Operator {
 
 struct MGLevel {
   Operator op;
-  Field b, xa, xb, r, d;
+  Field b, xa, xb, r;
   // coarsest level
   int n_dense = 0;
   double* Ainv = nullptr;

@@ -74,7 +74,8 @@ struct SweepArgs {
   const double* x;
   const double* b;
   double* y;
-  double* d;
+  const double* xprev;  // Chebyshev: previous iterate (may alias y); d_{k-1} = x_k - x_{k-1} is never stored
+  int prev_mode;        // 0 restart, 1 xprev pointer, 2 previous iterate is zero, 3 previous iterate = s0*dinv*b
   double bconst[3];
   double bscale, ascale, c1, c2, s0;
   double load_int;    // load of the interior class
@@ -164,7 +165,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
           ReduceBuf red, double* red_out) {
   constexpr bool CHEBY = MODE >= M_CHEBY;
   constexpr bool HAS_B = MODE == M_RESID || MODE == M_CHEBY;
-  constexpr bool LOAD_D = MODE == M_CHEBY;
+  constexpr bool LOAD_D = MODE == M_CHEBY;  // loads x_{k-1} (prev_mode 1) to rebuild the direction
   constexpr bool XQ_REG = NC == 1;  // own-column queue in registers; vector kernels re-read x (L2 hit) instead
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* stage0 = reinterpret_cast<double*>(smem_raw);
@@ -282,14 +283,14 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const double* __restrict__ bp = HAS_B ? a.b + (long long)g.plane * zout + c * g.comp_stride : nullptr;
-        const double* __restrict__ dp = LOAD_D ? a.d + (long long)g.plane * zout + c * g.comp_stride : nullptr;
+        const double* dp = (LOAD_D && a.prev_mode == 1) ? a.xprev + (long long)g.plane * zout + c * g.comp_stride : nullptr;
         const double* __restrict__ xp = a.x + (long long)g.plane * zout + c * g.comp_stride;
 #pragma unroll
         for (int j = 0; j < YS; ++j) {
           const bool ok = (valid >> j) & 1u;
           const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
           if (HAS_B) bv[j][c] = ok ? bp[off] : 0.0;
-          if (LOAD_D) dv[j][c] = ok ? dp[off] : 0.0;
+          if (LOAD_D) dv[j][c] = (ok && dp) ? dp[off] : 0.0;   // x_{k-1}
           if (!XQ_REG) xv[j][c] = ok ? xp[off] : 0.0;
         }
       }
@@ -348,9 +349,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
       // interior-class rows: Dirichlet / out-of-range / face rows are masked by m = 0
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const double* __restrict__ dcp = CHEBY ? a.d + pbase + c * g.comp_stride : nullptr;
-        double* __restrict__ dp = const_cast<double*>(dcp);
-        double* __restrict__ yp = a.y ? a.y + pbase + c * g.comp_stride : nullptr;
+        double* yp = a.y ? a.y + pbase + c * g.comp_stride : nullptr;  // may alias xprev: no __restrict__
         const double bB = a.bscale * a.bconst[c] * a.load_int;  // constant load term of the interior class
         const double c2d = a.c2 * a.dinv_int[c];
         const double s0d = a.s0 * a.dinv_int[c];
@@ -365,13 +364,17 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
             const double d1 = s0d * bi;
             const double dn = m * fma(a.c1, d1, c2d * fma(-s0d, aP[j][c], bi));
             const double yv = m * d1 + dn;
-            if (on) { dp[off] = dn; yp[off] = yv; }
+            if (on) yp[off] = yv;
             red_xy = fma(bi, yv, red_xy);
           } else if (CHEBY) {
             const double B = bv[j][c];
-            const double dn = m * fma(a.c1, dv[j][c], c2d * (B - aP[j][c]));
-            const double yv = xv[j][c] + dn;
-            if (on) { dp[off] = dn; yp[off] = yv; }
+            const double xo = xv[j][c];
+            // direction of the previous sweep, rebuilt from the iterates
+            const double dprev = a.prev_mode == 1 ? xo - dv[j][c]
+                               : (a.prev_mode == 2 ? xo : (a.prev_mode == 3 ? xo - s0d * B : 0.0));
+            const double dn = m * fma(a.c1, dprev, c2d * (B - aP[j][c]));
+            const double yv = xo + dn;
+            if (on) yp[off] = yv;
             red_xy = fma(m * B, yv, red_xy);
           } else {
             const double yv = m * (HAS_B ? fma(a.ascale, aP[j][c], a.bscale * bv[j][c]) : fma(a.ascale, aP[j][c], bB));
@@ -527,7 +530,7 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   for (int k = 0; k < PDE_NOFF; ++k)
     for (int q = 0; q < NC * NC; ++q) C.c[k][q] = op.h_int[k * NC * NC + q];
   SweepArgs sa;
-  sa.x = a.x; sa.b = a.b; sa.y = a.y; sa.d = a.d;
+  sa.x = a.x; sa.b = a.b; sa.y = a.y; sa.xprev = a.xprev; sa.prev_mode = a.prev_mode;
   for (int i = 0; i < 3; ++i) sa.bconst[i] = a.bconst[i];
   sa.bscale = a.bscale; sa.ascale = a.ascale; sa.c1 = a.c1; sa.c2 = a.c2; sa.s0 = a.s0;
   sa.load_int = op.h_load_int;
