@@ -186,6 +186,13 @@ int pde_op_bench(pde_ctx* ctx, const pde_op_params* p, int reps, int warmup, dou
 int pde_op_solve(pde_ctx* ctx, const pde_op_params* p, const pde_solver_opts* o, const double* b,
                  double* x, pde_stats* st);
 
+/* Device-resident manufactured-solution check for sizes no CPU oracle can reach (SURVEY §8c iv-c):
+ * u*_i = sin(0.37 i + comp) + 0.5 on free nodes (0 on Dirichlet nodes), b = A u* with the matrix-free
+ * operator, solve A x = b from x = 0 with the configured PCG, return ||x - u*||_2 / ||u*||_2.
+ * Nothing but scalars crosses the host boundary. */
+int pde_op_manufactured(pde_ctx* ctx, const pde_op_params* p, const pde_solver_opts* o, double* rel_l2_error,
+                        pde_stats* st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -596,6 +596,64 @@ extern "C" int pde_op_solve(pde_ctx* c, const pde_op_params* p, const pde_solver
   return 0;
 }
 
+extern "C" int pde_op_manufactured(pde_ctx* c, const pde_op_params* p, const pde_solver_opts* o_in, double* rel_err,
+                                   pde_stats* st_out) {
+  if (!c || !p || !rel_err) PDE_FAIL("null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  pde_solver_opts o;
+  if (o_in) o = *o_in; else pde_solver_opts_default(&o);
+  OpGuard G;
+  Field ustar;
+  struct Rel { Field* f; ~Rel() { f->release(); } } rel{&ustar};
+  int nc;
+  PDE_OK(setup_op(c, p, &G.A, &nc));
+  const Grid& g = G.A.g;
+  PDE_OK(ustar.alloc(c, g, nc));
+  PDE_OK(G.x.alloc(c, g, nc));
+  PDE_OK(G.y.alloc(c, g, nc));   // b
+  PDE_OK(G.r.alloc(c, g, nc));
+  PDE_OK(launch_fill_pattern(c, g, G.A.bc, nc, ustar.p));
+  // b = A u*  (also ||b||^2)
+  StencilArgs a;
+  a.x = ustar.p; a.y = G.y.p; a.reduce_slot_xy = S_XY;
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, ustar.p));
+  PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
+  double bn2;
+  PDE_OK(read_scal(c, S_YY, 1, &bn2));
+  PDE_OK(launch_copy(c, g, nc, G.r.p, G.y.p));   // x0 = 0  =>  r0 = b
+  pde_stats st;
+  stats_init(&st, (long long)g.nn[0] * g.nn[1] * g.nzg * nc);
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  const long long l0 = c->launches;
+  PDE_OK(solve_with(c, G, p, o, G.x.p, G.r.p, bn2, &st));
+  // true residual ||b - A x|| / ||b||
+  StencilArgs t;
+  t.x = G.x.p; t.b = G.y.p; t.y = nullptr; t.bscale = 1.0; t.ascale = -1.0; t.reduce_slot_xy = S_XY;
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, G.x.p));
+  PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, t));
+  if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
+  double rr;
+  PDE_OK(read_scal(c, S_YY, 1, &rr));
+  st.true_relres = bn2 > 0 ? std::sqrt(rr / bn2) : 0.0;
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  st.solve_ms = ms - st.setup_ms;
+  st.launches = c->launches - l0;
+  // error norm: e = x - u*
+  PDE_OK(launch_axpy(c, g, nc, G.x.p, ustar.p, -1.0));
+  PDE_OK(launch_dot(c, g, nc, G.x.p, G.x.p, S_TMP0));
+  PDE_OK(launch_dot(c, g, nc, ustar.p, ustar.p, S_TMP1));
+  if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_TMP0, 2));
+  double v[2];
+  PDE_OK(read_scal(c, S_TMP0, 2, v));
+  *rel_err = v[1] > 0 ? std::sqrt(v[0] / v[1]) : 0.0;
+  if (st_out) *st_out = st;
+  return 0;
+}
+
 // ---- elasticity -----------------------------------------------------------------------------------------
 extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const pde_solver_opts* o_in,
                                     double* field_out, double* disp_out, pde_stats* st_out, pde_stats* st_proj_out) {

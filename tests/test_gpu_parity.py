@@ -236,3 +236,37 @@ def test_manufactured_solution_large(P, ctx, kind, n, precond):
     x, st = P._lib.op_solve(ctx, p, b, P._lib.make_opts(rtol=1e-11, precond=precond))
     assert st["converged"] == 1 and st["true_relres"] < 1e-9
     assert fo.rel_l2(x, us) <= TOL, fo.rel_l2(x, us)
+
+
+# ---------------------------------------------------------------- BASELINE full sizes: device-resident properties
+@pytest.mark.parametrize("kind,n,L,faces", [
+    ("heat", [512, 512, 512], [1.0, 1.0, 1.0], {f: 0.0 for f in range(6)}),          # config 4
+    ("elasticity", [1280, 256, 256], [1.0, 0.2, 0.2], {0: 0.0}),                      # config 5
+    ("heat", [4096, 4096], [1.0, 1.0], {f: 0.0 for f in range(4)}),                   # config 2
+    ("elasticity", [320, 64, 64], [1.0, 0.2, 0.2], {0: 0.0}),                         # config 3
+    ("heat", [333, 77, 130], [1.0, 0.3, 0.4], {0: 0.0, 3: 0.0}),                      # ragged tiles, mixed BCs
+])
+def test_manufactured_solution_full_size(P, ctx, kind, n, L, faces):
+    # (iv-c) at the sizes BASELINE.json names: b = A u* on the device, GMG/Jacobi-PCG to rtol 1e-11, ||x-u*||/||u*||
+    dim = len(n)
+    lam, mu = fo.lame(210e9, 0.3, 3)
+    p = P._lib.op_params(kind, dim, n, L, 1.0, 0.01, lam, mu, bc=P._lib.make_bc(faces))
+    err, st = P._lib.op_manufactured(ctx, p, P._lib.make_opts(rtol=1e-11, precond="auto"))
+    assert st["converged"] == 1 and st["true_relres"] < 1e-9, st
+    assert err <= TOL, (err, st)
+
+
+def test_multi_gpu_slabs_match_oracle():
+    """2-rank slab-partitioned GMG / Jacobi heat solve against the oracle (skipped on a 1-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "scripts", "mgpu_check.py")], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0 and "MGPU OK" in r.stdout, r.stdout[-3000:]
