@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpde_b200.so")
 SOURCES = ["tables.cpp", "kernels.cu", "stencil3d.cu", "solver.cu", "comm.cu", "cabi.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("PDE_B200_NVCC_FLAGS", "").split()
 
 
 def _newest(paths):

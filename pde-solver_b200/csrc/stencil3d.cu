@@ -158,8 +158,22 @@ __device__ __forceinline__ void plane_contrib(const Coef<NC>& C, const double (&
 // Chebyshev sweeps from a zero guess (input field = right-hand side; needs a uniform Jacobi diagonal)
 enum { M_APPLY = 0, M_RESID = 1, M_CHEBY = 2, M_FIRST2 = 3 };
 
+// launch bounds, tuned on B200 (A/B builds): scalar kernel 192 threads x >= 3 CTAs/SM (<= 113 registers);
+// the vector kernel is better left unconstrained (254 registers, 2 CTAs of 128 threads)
+#ifndef SW_MAXT1
+#define SW_MAXT1 192
+#endif
+#ifndef SW_MAXT3
+#define SW_MAXT3 256
+#endif
+#ifndef SW_MINB1
+#define SW_MINB1 3
+#endif
+#ifndef SW_MINB3
+#define SW_MINB3 1
+#endif
 template <int NC, int YS, int MODE, bool SPEC>
-__global__ void __launch_bounds__(NC == 1 ? 384 : 256)
+__global__ void __launch_bounds__(NC == 1 ? SW_MAXT1 : SW_MAXT3, NC == 1 ? SW_MINB1 : SW_MINB3)
 k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
           const __grid_constant__ Coef<NC> C, const __grid_constant__ SweepArgs a, const __grid_constant__ SweepGeom sw,
           ReduceBuf red, double* red_out) {
@@ -489,12 +503,12 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   sw.spec = SPEC ? 1 : 0;
   int txmax = tu.txmax > 0 ? tu.txmax : (NC == 1 ? 192 : 64);  // tuned on B200: heat 512^3, elasticity 1280x256x256
   txmax = txmax < 32 ? 32 : (txmax > 254 ? 254 : txmax);
-  if (txmax > (NC == 1 ? 384 : 256) - 34) txmax = (NC == 1 ? 384 : 256) - 34;
+  if (txmax > (NC == 1 ? SW_MAXT1 : SW_MAXT3) - 34) txmax = (NC == 1 ? SW_MAXT1 : SW_MAXT3) - 34;
   sw.ntx = (g.nn[0] + txmax - 1) / txmax;
   sw.tx = (g.nn[0] + sw.ntx - 1) / sw.ntx;
   sw.tx += sw.tx & 1;  // even: the TMA box row must be a multiple of 16 bytes
   sw.ntx = (g.nn[0] + sw.tx - 1) / sw.tx;
-  const int maxnt = (NC == 1 ? 384 : 256) - (SPEC ? 32 : 0);  // a producer warp is extra
+  const int maxnt = (NC == 1 ? SW_MAXT1 : SW_MAXT3) - (SPEC ? 32 : 0);  // a producer warp is extra
   int nt_target = tu.nt > 0 ? tu.nt : (NC == 1 ? 192 : 128);
   nt_target = nt_target < 64 ? 64 : (nt_target > maxnt ? maxnt : nt_target);
   sw.ns = nt_target / sw.tx;
