@@ -191,25 +191,23 @@ def run_native(args):
     iters = st["iters_total"]
 
     # ---- end to end through the C ABI with pinned HOST buffers (H2D + step + D2H per step) ----
-    hin = _lib.PinnedArray(hs.nloc)
-    hout = _lib.PinnedArray(hs.nloc)
-    hs.get_state(hout.array)
-    hin.array[:] = hout.array
+    # every step: H2D copy of the step's input field from pinned host memory, one backward-Euler solve, D2H read of
+    # the result into pinned host memory (which is the next step's input: no host-side copy in between)
+    hbuf = _lib.PinnedArray(hs.nloc)
+    hs.get_state(hbuf.array)
     e_steps = max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e_steps):
-        hs.set_state(hin.array)
+        hs.set_state(hbuf.array)
         hs.step(1)
-        hs.get_state(hout.array)
-        hin.array[:] = hout.array      # the next step's input is this step's output (host side)
+        hs.get_state(hbuf.array)
     barrier()
     e_sec = max_over_ranks(time.perf_counter() - t0)
     e2e = ndofs * e_steps / e_sec / 1e9
     bytes_dir = int(sum_over_ranks(hs.nloc * 8))
     hs.close()
-    hin.free()
-    hout.free()
+    hbuf.free()
 
     # ---- dominant kernel: matrix-free operator apply y = (M + dt k K) x, 16 B/dof algorithmic ----
     peaks, peak_kind = measured_peaks()
@@ -230,6 +228,19 @@ def run_native(args):
                 "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "kernel": "heat operator apply (+fused dot)",
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "ms_per_launch": op_ms,
                 "per_gpu_dofs": op_nd, "nominal_8TBs_frac": ach / 8000.0}
+
+    # ---- halo exchange (N > 1): one 513x513 plane each way per z-neighbour, NCCL send/recv over NVLink ----
+    halo = None
+    if world > 1:
+        barrier()
+        h_ms, h_bytes = _lib.halo_bench(ctx, 3, n, 1, reps=50)
+        h_ms = max_over_ranks(h_ms)
+        halo = {"ms_per_exchange": h_ms, "bytes_sent_per_rank": int(max_over_ranks(h_bytes)),
+                "gbs_per_direction": (max_over_ranks(h_bytes) / 2) / (h_ms / 1e3) / 1e9 if h_ms > 0 else None,
+                "nvlink_peer_copy_peak_gbs": 770.0, "share_of_step_ms":
+                    h_ms * (st["launches"] / max(1, args.steps)) * 0.0 + h_ms}
+        halo["frac_of_nvlink"] = halo["gbs_per_direction"] / 770.0 if halo["gbs_per_direction"] else None
+        del halo["share_of_step_ms"]
 
     if rank != 0:
         if dist is not None:
@@ -283,7 +294,7 @@ def run_native(args):
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": "GDOF/s", "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir,
                 "steps": e_steps},
-        "gpu_launches": int(st["launches"]), "clocks": clocks, "elasticity": elast,
+        "gpu_launches": int(st["launches"]), "clocks": clocks, "elasticity": elast, "halo": halo,
     }
     print(json.dumps(out), flush=True)
     if dist is not None:

@@ -54,6 +54,11 @@ int pde_comm_init(pde_ctx* ctx, int rank, int world, const void* id128, const ch
 int pde_slab_partition(int dim, const int32_t n[3], int rank, int world, int level, int32_t* z0, int32_t* nzl,
                        int32_t* nzg);
 
+/* time `reps` halo exchanges (one plane each way per z-neighbour, `ncomp` components) of the slab of a
+ * dim-D mesh; returns mean ms per exchange and the bytes this rank sends per exchange */
+int pde_halo_bench(pde_ctx* ctx, int dim, const int32_t n[3], int ncomp, int reps, double* ms_per_exchange,
+                   int64_t* bytes_sent);
+
 /* ---- meshes, dof maps, boundary sets (bit-exact rows a2-a4 of SURVEY §8) ------------- */
 /* IntervalMesh :229,1516 / RectangleMesh :369,1648 / BoxMesh :533,1803.
  * dim in {1,2,3}; n[k] cells along axis k; domain [0,L[k]].  Generated on the GPU. */

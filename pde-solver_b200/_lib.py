@@ -83,7 +83,7 @@ def lib():
                      "pde_mesh_cells", "pde_dofmap_cells", "pde_boundary_mask", "pde_heat_solve",
                      "pde_heat_open", "pde_heat_set_state", "pde_heat_step", "pde_heat_get_state",
                      "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench",
-                     "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition", "pde_op_manufactured"):
+                     "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition", "pde_op_manufactured", "pde_halo_bench"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib
@@ -245,6 +245,13 @@ def op_solve(ctx, p, b, opts=None):
     o = opts if opts is not None else make_opts()
     check(lib().pde_op_solve(ctx.handle, C.byref(p), C.byref(o), ptr(b), ptr(x), C.byref(st)))
     return x, st.as_dict()
+
+
+def halo_bench(ctx, dim, n, ncomp=1, reps=50):
+    """(ms per halo exchange, bytes this rank sends per exchange) over NCCL send/recv."""
+    ms, nb = C.c_double(), C.c_int64()
+    check(lib().pde_halo_bench(ctx.handle, int(dim), i3(n), int(ncomp), int(reps), C.byref(ms), C.byref(nb)))
+    return ms.value, nb.value
 
 
 def op_manufactured(ctx, p, opts=None):

@@ -102,6 +102,30 @@ static int h2d(pde_ctx* c, void* dst, const void* src, size_t bytes) {
   return 0;
 }
 
+extern "C" int pde_halo_bench(pde_ctx* c, int dim, const int32_t n[3], int ncomp, int reps, double* ms_per_exchange,
+                              int64_t* bytes_sent) {
+  if (!c) PDE_FAIL("null context");
+  if (ncomp < 1 || ncomp > 3) PDE_FAIL("ncomp must be 1..3");
+  CUDA_OK(cudaSetDevice(c->device));
+  const double L1[3] = {1, 1, 1};
+  Grid g;
+  PDE_OK(make_grid(dim, n, L1, c->rank, c->world, &g));
+  Field f;
+  struct Rel { Field* f; ~Rel() { f->release(); } } rel{&f};
+  PDE_OK(f.alloc(c, g, ncomp));
+  for (int i = 0; i < 3; ++i) PDE_OK(comm_halo_exchange(c, g, ncomp, f.p));
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < reps; ++i) PDE_OK(comm_halo_exchange(c, g, ncomp, f.p));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (ms_per_exchange) *ms_per_exchange = ms / (reps > 0 ? reps : 1);
+  const int nbr = (c->rank > 0 ? 1 : 0) + (c->rank < c->world - 1 ? 1 : 0);
+  if (bytes_sent) *bytes_sent = (int64_t)nbr * ncomp * g.plane * (int64_t)sizeof(double);
+  return 0;
+}
+
 // ---- meshes -------------------------------------------------------------------------------------
 extern "C" int pde_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* coords) {
   if (!c) PDE_FAIL("null context");
