@@ -235,12 +235,12 @@ def run_native(args):
         barrier()
         h_ms, h_bytes = _lib.halo_bench(ctx, 3, n, 1, reps=50)
         h_ms = max_over_ranks(h_ms)
-        halo = {"ms_per_exchange": h_ms, "bytes_sent_per_rank": int(max_over_ranks(h_bytes)),
-                "gbs_per_direction": (max_over_ranks(h_bytes) / 2) / (h_ms / 1e3) / 1e9 if h_ms > 0 else None,
-                "nvlink_peer_copy_peak_gbs": 770.0, "share_of_step_ms":
-                    h_ms * (st["launches"] / max(1, args.steps)) * 0.0 + h_ms}
-        halo["frac_of_nvlink"] = halo["gbs_per_direction"] / 770.0 if halo["gbs_per_direction"] else None
-        del halo["share_of_step_ms"]
+        plane_bytes = (((n[0] + 2 + 3) // 4) * 4) * (n[1] + 2) * 8      # one padded vertex plane
+        gbs = plane_bytes / (h_ms / 1e3) / 1e9 if h_ms > 0 else None
+        halo = {"ms_per_exchange": h_ms, "plane_bytes": plane_bytes, "bytes_sent_per_rank_max": int(max_over_ranks(h_bytes)),
+                "gbs_per_direction": gbs, "nvlink_peer_copy_peak_gbs": 770.0,
+                "frac_of_nvlink": gbs / 770.0 if gbs else None,
+                "note": "grouped ncclSend/ncclRecv of one contiguous plane per neighbour; latency-bound at this size"}
 
     if rank != 0:
         if dist is not None:

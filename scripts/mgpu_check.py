@@ -86,7 +86,7 @@ if rank == 0:
     ok = ok and e_vm <= 1e-8 and e_u <= 1e-8 and st.converged == 1
 h_ms, h_bytes = _lib.halo_bench(ctx, 3, [512, 512, 64 * world], 1, reps=50)
 if rank == 0:
-    print(f"[mgpu] halo exchange 513x513 plane: {h_ms * 1e3:.1f} us, {h_bytes / 2 / (h_ms / 1e3) / 1e9:.0f} GB/s per direction",
+    print(f"[mgpu] halo exchange 513x513 plane: {h_ms * 1e3:.1f} us, {516 * 514 * 8 / (h_ms / 1e3) / 1e9:.0f} GB/s per direction",
           flush=True)
     print("MGPU OK" if ok else "MGPU FAIL", flush=True)
 dist.barrier()
