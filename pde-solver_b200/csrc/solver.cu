@@ -265,9 +265,15 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
     bool can = true;
     if (const char* ml = getenv("PDE_B200_MAX_LEVELS")) can = can && (level + 1 < atoi(ml));
     int32_t nc2[3] = {0, 0, 0};
+    // vector (elasticity) operators: re-discretised P1 operators on grids with a single cell across the body are
+    // far too stiff in bending (locking), which spoils the coarse correction (33 -> ~20 PCG iterations on the
+    // cantilever when the hierarchy stops at two cells across); scalar operators coarsen down to one cell
+    static const int env_min = getenv("PDE_B200_MIN_COARSE_CELLS") ? atoi(getenv("PDE_B200_MIN_COARSE_CELLS")) : 0;
+    const int min_cells = env_min > 0 ? env_min : (ncomp > 1 ? 2 : 1);
     for (int q = 0; q < nax; ++q) {
       if (n[q] % 2 != 0 || n[q] < 2) can = false;
       nc2[q] = n[q] / 2;
+      if (nc2[q] < min_cells) can = false;
     }
     // slabs: the coarse partition must nest in the fine one (rank r owns coarse planes z0/2 ...)
     if (c->world > 1 && n[nax - 1] % (2 * c->world) != 0) can = false;
