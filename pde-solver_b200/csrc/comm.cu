@@ -101,18 +101,20 @@ int comm_allreduce_buf(pde_ctx* c, double* buf, size_t count) {
   return 0;
 }
 
-int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* f) {
+int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* f, int depth) {
   if (c->world == 1) return 0;
-  const size_t n = (size_t)g.plane;
+  if (depth < 1 || depth > PDE_NG) PDE_FAIL("halo depth out of range");
+  if (depth > g.nzl) PDE_FAIL("halo deeper than the slab");
+  const size_t n = (size_t)g.plane * depth;   // `depth` consecutive planes are contiguous
   NCCL_OK(c->nccl->GroupStart());
   for (int i = 0; i < ncomp; ++i) {
     double* b = f + (size_t)i * g.comp_stride;
     if (c->rank > 0) {
-      NCCL_OK(c->nccl->Send(b, n, 8, c->rank - 1, c->nccl_comm, c->stream));                   // my first plane
-      NCCL_OK(c->nccl->Recv(b - g.plane, n, 8, c->rank - 1, c->nccl_comm, c->stream));         // lower ghost
+      NCCL_OK(c->nccl->Send(b, n, 8, c->rank - 1, c->nccl_comm, c->stream));                          // my first planes
+      NCCL_OK(c->nccl->Recv(b - (size_t)depth * g.plane, n, 8, c->rank - 1, c->nccl_comm, c->stream));  // lower ghosts
     }
     if (c->rank < c->world - 1) {
-      NCCL_OK(c->nccl->Send(b + (size_t)(g.nzl - 1) * g.plane, n, 8, c->rank + 1, c->nccl_comm, c->stream));
+      NCCL_OK(c->nccl->Send(b + (size_t)(g.nzl - depth) * g.plane, n, 8, c->rank + 1, c->nccl_comm, c->stream));
       NCCL_OK(c->nccl->Recv(b + (size_t)g.nzl * g.plane, n, 8, c->rank + 1, c->nccl_comm, c->stream));
     }
   }

@@ -3,7 +3,7 @@
 // HBM layout of a nodal field (one displacement/temperature component):
 //   node (ix,iy,iz) lives at  base + ix + PX*(iy + PY*iz)
 //   PX >= nnx+1 (multiple of 4 doubles: 32-byte aligned rows, TMA-legal pitch), PY = nny+1
-//   (PY = 1 when the y axis is absent).  One zero "ghost" plane sits before plane 0 and one
+//   (PY = 1 when the y axis is absent).  PDE_NG zero "ghost" planes sit before plane 0 and
 //   after the last plane; every pad column / pad row / ghost plane stays ZERO in all vectors,
 //   so a stencil read that leaves the domain (including the x/y wrap into the previous row /
 //   plane) reads 0 and no bounds test is needed.  With slab partitioning the two ghost planes
@@ -18,6 +18,9 @@
 
 #include "../../include/pde_b200.h"
 
+// ghost planes kept before plane 0 and after the last plane of every field component (zero at the domain
+// ends, halo planes between slabs).  Depth 2 lets the temporally blocked smoother run two sweeps per pass.
+#define PDE_NG 2
 #define PDE_NCLASS 27
 #define PDE_NOFF 15
 
@@ -31,7 +34,7 @@ struct Grid {
   int nzg;          // global planes
   long long plane;  // PX*PY
   long long total;  // plane*nzl : flat length of one component (without ghost planes)
-  long long comp_stride;  // plane*(nzl+2)
+  long long comp_stride;  // plane*(nzl+2*PDE_NG)
   double h[3];
   int nk;                 // active stencil offsets
   int kidx[PDE_NOFF];     // active offset ids

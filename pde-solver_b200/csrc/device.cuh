@@ -179,6 +179,9 @@ struct StencilArgs {
 };
 
 int launch_stencil(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
+// two restart Chebyshev sweeps in one pass (temporal blocking); *handled = false if not applicable
+int launch_post2(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* x0, const double* b,
+                 double* y, double c2_0, double c1_1, double c2_1, int dot_slot, bool* handled);
 // rows of the non-Dirichlet nodes on the domain faces (class-table stencil); reductions are ADDED to the slot
 int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
 // Jacobi-PCG fused update: x += a p, r -= a q, rho_new = r.dinv r, rr = r.r  (a = rho/pAp from scal)
@@ -222,5 +225,6 @@ int launch_bc_mask(pde_ctx* c, const Grid& g, const BcDev& bc, uint8_t* mask, do
 
 // comm.cu
 int comm_allreduce_scal(pde_ctx* c, int slot, int count);
-int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* field);
+// exchange `depth` (<= PDE_NG) boundary planes with the z-neighbours into the ghost planes
+int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* field, int depth = 1);
 int comm_allreduce_buf(pde_ctx* c, double* buf, size_t count);

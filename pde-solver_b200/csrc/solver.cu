@@ -32,7 +32,7 @@ int Field::alloc(pde_ctx* c, const Grid& g, int ncomp) {
   // zero on the context's stream: it is a non-blocking stream, so a legacy-stream cudaMemset would
   // not be ordered against the kernels that use this field
   CUDA_OK(cudaMemsetAsync(raw, 0, bytes, c->stream));
-  p = raw + lead + g.plane;
+  p = raw + lead + PDE_NG * g.plane;
   return 0;
 }
 void Field::release() {
@@ -373,6 +373,25 @@ static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double*
     PDE_OK(launch_cheby_first(c, L.op.g, L.op.bc, L.op.dev, b, *cur, c2));
     k0 = 1;
     prev_mode = 2;     // x_0 = 0
+  }
+  if (!zero_guess && sweeps == 2 && L.op.dev.uniform_diag && L.op.dev.ncomp == 1 &&
+      (c->world == 1 || L.op.g.nzl >= PDE_NG)) {
+    // both sweeps in one pass over the data (needs two halo planes of the iterate and one of the rhs)
+    double c1a, c2a, c1b, c2b;
+    ch.coef(0, &c1a, &c2a);
+    ch.coef(1, &c1b, &c2b);
+    bool handled = false;
+    if (c->world > 1) {
+      PDE_OK(comm_halo_exchange(c, L.op.g, 1, *cur, PDE_NG));
+      PDE_OK(comm_halo_exchange(c, L.op.g, 1, const_cast<double*>(b), 1));
+    }
+    PDE_OK(launch_post2(c, L.op.g, L.op.bc, L.op.dev, *cur, b, *oth, c2a, c1b, c2b, dot_slot, &handled));
+    if (handled) {
+      std::swap(*cur, *oth);
+      if (dot_slot >= 0 && dot_done) *dot_done = true;
+      return 0;
+    }
+    ch.init(L.op.dev.gershgorin, ratio);  // not applicable: fall through to the separate sweeps
   }
   for (int k = k0; k < sweeps; ++k) {
     StencilArgs a;

@@ -217,7 +217,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
   if (!spec && t == 0) {
     for (int i = 0; i < SW_STAGES && i < nplanes; ++i) {
       mbar_expect_tx(bar0 + 8 * i, stage_bytes);
-      tma_load_4d(stg0 + i * stage_stride, &tmx, x0 - 2, y0 - 1, za + i, 0, bar0 + 8 * i);
+      tma_load_4d(stg0 + i * stage_stride, &tmx, x0 - 2, y0 - 1, za + i - 1 + PDE_NG, 0, bar0 + 8 * i);
     }
   }
   if (spec && (t >> 5) == ncw) {
@@ -227,9 +227,9 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
         const int stage = i % SW_STAGES;
         if (i >= SW_STAGES) mbar_wait(ebar0 + 8 * stage, (uint32_t)(((i / SW_STAGES) - 1) & 1));
         mbar_expect_tx(bar0 + 8 * stage, stage_bytes);
-        // tensor z coordinate: ghost plane is z=0, local plane lz is z=lz+1.  The box starts at x0-2: TMA needs
+        // tensor z coordinate: local plane lz is z = lz + PDE_NG (the ghost planes come first).  The box starts at x0-2: TMA needs
         // the inner start coordinate 16-byte aligned (even for FP64); x0-1 raises an illegal-instruction fault
-        tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i, 0, bar0 + 8 * stage);
+        tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i - 1 + PDE_NG, 0, bar0 + 8 * stage);
       }
     }
     if (a.do_reduce) {  // the block reduction below is CTA-wide
@@ -346,7 +346,7 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
       __syncthreads();  // every thread has consumed this stage
       if (t == 0 && i + SW_STAGES < nplanes) {
         mbar_expect_tx(bar0 + 8 * stage, stage_bytes);
-        tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i + SW_STAGES, 0, bar0 + 8 * stage);
+        tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 1, za + i + SW_STAGES - 1 + PDE_NG, 0, bar0 + 8 * stage);
       }
     }
     if (FIN) {
@@ -423,6 +423,211 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
   }
 }
 
+// ----------------------------------------------------------------------------------------------------
+// k_post2: TWO Chebyshev-Jacobi sweeps in ONE pass over the data (temporal blocking), for scalar operators
+// whose free nodes all carry the interior stencil (every face Dirichlet):
+//     d0 = a0 (b - A x0),  x1 = x0 + d0 ;   d1 = c1 d0 + a1 (b - A x1),  x2 = x1 + d1        (a_k = c2_k / diag)
+// reads x0 and b, writes x2: 24 B/dof instead of 24 + 32 for two separate sweeps.
+//   Stage A runs the plane sweep on the output tile grown by one node in x and y (and one plane in z) and
+//   leaves x1, d0 of the plane it retires in a 3-slot shared-memory ring; stage B runs the same plane sweep on
+//   that ring, one plane behind, and retires x2.  A thread owns column c of the grown tile in both stages, a
+//   strip of YSB+1 rows in stage A and YSB rows in stage B; TY = 2*YSB rows of output per tile.
+//   Input planes za-2 .. zb+1 are needed for outputs za .. zb-1: fields carry PDE_NG = 2 ghost planes.
+// ----------------------------------------------------------------------------------------------------
+#define P2_MAXT 192
+#define P2_MINB 2
+
+struct Post2Geom {
+  int tx, ty;          // output tile
+  int cw, ra;          // grown tile: tx+2 columns, ty+2 rows
+  int bx, by;          // TMA box (tx+4, ty+4), origin (x0-2, y0-2)
+  int ntx, nty, nzc, zc;
+  int stage_elems;     // doubles per TMA stage (multiple of 16)
+  int ring_elems;      // doubles per ring slot (cw*ra rounded up)
+};
+struct Post2Args {
+  const double* b;
+  double* y;
+  double a0, c1, a1;
+  int do_reduce;
+};
+
+template <int YSB>
+__global__ void __launch_bounds__(P2_MAXT, P2_MINB)
+k_post2(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid g, const __grid_constant__ Coef<1> C,
+        const __grid_constant__ Post2Args a, const __grid_constant__ Post2Geom pg, ReduceBuf red, double* red_out) {
+  constexpr int YSA = YSB + 1;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* stage0 = reinterpret_cast<double*>(smem_raw);
+  double* x1ring = stage0 + (size_t)SW_STAGES * pg.stage_elems;
+  double* d0ring = x1ring + 3 * (size_t)pg.ring_elems;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(d0ring + 3 * (size_t)pg.ring_elems);
+
+  const int t = threadIdx.x;
+  const int item = blockIdx.x;
+  const int itx = item % pg.ntx;
+  const int ity = (item / pg.ntx) % pg.nty;
+  const int izc = item / (pg.ntx * pg.nty);
+  const int x0 = itx * pg.tx, y0 = ity * pg.ty;
+  const int za = izc * pg.zc;
+  const int zb = min(za + pg.zc, g.nzl);
+  const int nplanes = zb - za + 4;  // input planes za-2 .. zb+1
+  const uint32_t stage_bytes = (uint32_t)(pg.bx * pg.by * sizeof(double));
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t stg0 = smem_u32(stage0);
+  const uint32_t stage_stride = (uint32_t)(pg.stage_elems * sizeof(double));
+
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < SW_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0) {
+    for (int i = 0; i < SW_STAGES && i < nplanes; ++i) {
+      mbar_expect_tx(bar0 + 8 * i, stage_bytes);
+      tma_load_4d(stg0 + i * stage_stride, &tmx, x0 - 2, y0 - 2, za - 2 + i + PDE_NG, 0, bar0 + 8 * i);
+    }
+  }
+
+  const int c = t % pg.cw;           // column of the grown tile: x = x0 - 1 + c
+  int s = t / pg.cw;
+  const bool active = s < 2;
+  if (!active) s = 0;                // surplus threads shadow strip 0 and never store
+  const int ixA = x0 - 1 + c;
+  const int cB = min(max(c, 1), pg.cw - 2);  // stage-B column used for addressing (clamped for the two edge columns)
+  const bool colB = active && c >= 1 && c <= pg.tx && ixA < g.nn[0];
+  // stage A: rows rA = s*YSA + j of the grown tile (y = y0 - 1 + rA); stage B: rows rB = s*YSB + j (y = y0 + rB)
+  double mA[YSA], mB[YSB];
+  unsigned loadA = 0, validB = 0;
+  const bool xfree = ixA >= 1 && ixA <= g.nn[0] - 2;
+#pragma unroll
+  for (int j = 0; j < YSA; ++j) {
+    const int iy = y0 - 1 + s * YSA + j;
+    const bool f = active && xfree && iy >= 1 && iy <= g.nn[1] - 2;
+    mA[j] = f ? 1.0 : 0.0;
+    if (f) loadA |= 1u << j;
+  }
+#pragma unroll
+  for (int j = 0; j < YSB; ++j) {
+    const int iy = y0 + s * YSB + j;
+    const bool v = colB && iy < g.nn[1];
+    if (v) validB |= 1u << j;
+    mB[j] = (v && xfree && iy >= 1 && iy <= g.nn[1] - 2) ? 1.0 : 0.0;
+  }
+  const double* sbaseA = stage0 + (s * YSA) * pg.bx + c;                 // V[r][cc] = sbaseA[r*bx + cc]
+  const int ringA = (s * YSA) * pg.cw + c;                               // ring offset of stage-A row j: + j*cw
+  const int ringB = (s * YSB) * pg.cw + cB - 1;                          // VB[r][cc] = ring[ringB + r*cw + cc]
+  const int ringOwn = (s * YSB + 1) * pg.cw + cB;                        // own node of stage-B row j: + j*cw
+  const unsigned colA0 = (unsigned)((long long)g.PX * (y0 - 1 + s * YSA) + ixA);  // only used where loadA is set
+  const unsigned colB0 = (unsigned)((long long)g.PX * (y0 + s * YSB) + ixA);
+
+  double aA[YSA][1], aB[YSA][1], aC[YSA][1];     // stage-A accumulators (three planes in flight)
+  double bA_[YSB][1], bB_[YSB][1], bC_[YSB][1];  // stage-B accumulators
+  double xA[YSA], xB[YSA], xC[YSA];              // own-column x0 values of the resident / previous plane
+#pragma unroll
+  for (int j = 0; j < YSA; ++j) aA[j][0] = aB[j][0] = aC[j][0] = xA[j] = xB[j] = xC[j] = 0.0;
+#pragma unroll
+  for (int j = 0; j < YSB; ++j) bA_[j][0] = bB_[j][0] = bC_[j][0] = 0.0;
+  double red_xy = 0.0;
+
+  auto body = [&](int i, double (&aP)[YSA][1], double (&a0)[YSA][1], double (&aM)[YSA][1], double (&bP)[YSB][1],
+                  double (&b0)[YSB][1], double (&bM)[YSB][1], double (&xprev)[YSA], double (&xcur)[YSA]) {
+    const int stage = i % SW_STAGES;
+    const uint32_t parity = (uint32_t)((i / SW_STAGES) & 1);
+    const int q = za - 2 + i;        // resident input plane
+    const int pA = q - 1;            // plane stage A retires (x1, d0)
+    const int pB = q - 2;            // plane stage B retires (x2)
+    const bool finA = i >= 2, finB = i >= 4;
+    // early global loads of the right-hand side for the two retiring planes
+    double rhsA[YSA], rhsB[YSB];
+    if (finA) {
+      const double* bp = a.b + (long long)g.plane * pA;
+#pragma unroll
+      for (int j = 0; j < YSA; ++j) rhsA[j] = ((loadA >> j) & 1u) ? bp[colA0 + (unsigned)j * (unsigned)g.PX] : 0.0;
+    }
+    if (finB) {
+      const double* bp = a.b + (long long)g.plane * pB;
+#pragma unroll
+      for (int j = 0; j < YSB; ++j) rhsB[j] = ((validB >> j) & 1u) ? bp[colB0 + (unsigned)j * (unsigned)g.PX] : 0.0;
+    }
+    mbar_wait(bar0 + 8 * stage, parity);
+    {  // ---- stage A: plane q of x0 ----
+      double V[YSA + 2][3][1];
+      const double* sp = sbaseA + (size_t)stage * pg.stage_elems;
+#pragma unroll
+      for (int r = 0; r < YSA + 2; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          if ((r == 0 && cc == 2) || (r == YSA + 1 && cc == 0)) V[r][cc][0] = 0.0;  // never used
+          else V[r][cc][0] = sp[r * pg.bx + cc];
+        }
+#pragma unroll
+      for (int j = 0; j < YSA; ++j) xcur[j] = V[j + 1][1][0];
+      plane_contrib<1, YSA>(C, V, aP, a0, aM);
+    }
+    const int slotA = (pA + 3) % 3;
+    if (finA) {
+      const int gz = pA + g.z0;
+      const double mz = (gz >= 1 && gz <= g.nzg - 2) ? 1.0 : 0.0;
+      double* x1s = x1ring + (size_t)slotA * pg.ring_elems + ringA;
+      double* d0s = d0ring + (size_t)slotA * pg.ring_elems + ringA;
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < YSA; ++j) {
+          const double d0 = mA[j] * mz * a.a0 * (rhsA[j] - aP[j][0]);
+          x1s[j * pg.cw] = xprev[j] + d0;
+          d0s[j * pg.cw] = d0;
+        }
+      }
+    }
+    __syncthreads();  // the TMA stage is consumed and plane pA of x1 / d0 is visible
+    if (t == 0 && i + SW_STAGES < nplanes) {
+      mbar_expect_tx(bar0 + 8 * stage, stage_bytes);
+      tma_load_4d(stg0 + stage * stage_stride, &tmx, x0 - 2, y0 - 2, za - 2 + i + SW_STAGES + PDE_NG, 0, bar0 + 8 * stage);
+    }
+    if (finA) {  // ---- stage B: plane pA of x1 ----
+      double V[YSB + 2][3][1];
+      const double* rp = x1ring + (size_t)slotA * pg.ring_elems + ringB;
+#pragma unroll
+      for (int r = 0; r < YSB + 2; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+          if ((r == 0 && cc == 2) || (r == YSB + 1 && cc == 0)) V[r][cc][0] = 0.0;
+          else V[r][cc][0] = rp[r * pg.cw + cc];
+        }
+      plane_contrib<1, YSB>(C, V, bP, b0, bM);
+    }
+    if (finB) {
+      const int slotB = (pB + 3) % 3;
+      const int gz = pB + g.z0;
+      const double mz = (gz >= 1 && gz <= g.nzg - 2) ? 1.0 : 0.0;
+      const double* x1o = x1ring + (size_t)slotB * pg.ring_elems + ringOwn;
+      const double* d0o = d0ring + (size_t)slotB * pg.ring_elems + ringOwn;
+      double* yp = a.y + (long long)g.plane * pB;
+#pragma unroll
+      for (int j = 0; j < YSB; ++j) {
+        const double x1 = x1o[j * pg.cw], d0 = d0o[j * pg.cw];
+        const double d1 = mB[j] * mz * fma(a.c1, d0, a.a1 * (rhsB[j] - bP[j][0]));
+        const double x2 = x1 + d1;
+        if ((validB >> j) & 1u) yp[colB0 + (unsigned)j * (unsigned)g.PX] = x2;
+        red_xy = fma(mB[j] * mz * rhsB[j], x2, red_xy);
+      }
+    }
+  };
+
+  // stage-A roles rotate from step 0, stage-B roles from step 2 (its first plane): phase (i+1) mod 3
+  for (int i = 0; i < nplanes; i += 3) {
+    body(i, aA, aB, aC, bB_, bC_, bA_, xC, xA);
+    if (i + 1 < nplanes) body(i + 1, aB, aC, aA, bC_, bA_, bB_, xA, xB);
+    if (i + 2 < nplanes) body(i + 2, aC, aA, aB, bA_, bB_, bC_, xB, xC);
+  }
+  if (a.do_reduce) {
+    double v[1] = {red_xy};
+    block_reduce_finalize<1>(v, red, red_out);
+  }
+}
+
 // ---- host side: tensor maps, tile geometry, launch ---------------------------------------------------
 typedef CUresult (*PFN_tmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -459,21 +664,21 @@ struct TmKey {
   }
 };
 
-// Tensor map of a padded field: (x, y, z incl. both ghost planes, component); out-of-range x/y -> 0.
+// Tensor map of a padded field: (x, y, z incl. the ghost planes, component); out-of-range x/y -> 0.
 static int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by, CUtensorMap* out) {
   static std::map<TmKey, CUtensorMap> cache;
   static std::mutex mu;
-  TmKey k{(const void*)field, g.nn[0], g.nn[1], g.nzl + 2, nc, bx, by, g.PX, g.plane, g.comp_stride};
+  TmKey k{(const void*)field, g.nn[0], g.nn[1], g.nzl + 2 * PDE_NG, nc, bx, by, g.PX, g.plane, g.comp_stride};
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(k);
   if (it != cache.end()) { *out = it->second; return 0; }
   PFN_tmEncodeTiled enc = tm_encode_fn();
   if (!enc) PDE_FAIL("cuTensorMapEncodeTiled is not available from the CUDA driver");
-  cuuint64_t dims[4] = {(cuuint64_t)g.nn[0], (cuuint64_t)g.nn[1], (cuuint64_t)(g.nzl + 2), (cuuint64_t)nc};
+  cuuint64_t dims[4] = {(cuuint64_t)g.nn[0], (cuuint64_t)g.nn[1], (cuuint64_t)(g.nzl + 2 * PDE_NG), (cuuint64_t)nc};
   cuuint64_t strides[3] = {(cuuint64_t)g.PX * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.comp_stride * 8};
   cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1u, (cuuint32_t)nc};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  void* base = (void*)(field - g.plane);  // ghost plane below local plane 0
+  void* base = (void*)(field - PDE_NG * g.plane);  // first ghost plane below local plane 0
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) PDE_FAIL("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -556,6 +761,66 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   CUDA_OK(cudaGetLastError());
   // natural (non-Dirichlet) faces: their rows have incomplete element patches and come from the class table
   if (!op.uniform_diag) PDE_OK(launch_face_rows(c, g, bc, op, a));
+  return 0;
+}
+
+// Two Chebyshev sweeps (restart k = 0, 1) in one pass; returns *handled = false if the kernel does not apply.
+int launch_post2(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* x0, const double* b,
+                 double* y, double c2_0, double c1_1, double c2_1, int dot_slot, bool* handled) {
+  (void)bc;
+  *handled = false;
+  if (env_int("PDE_B200_NO_POST2", 0)) return 0;
+  if (g.dim != 3 || g.nk != PDE_NOFF || op.ncomp != 1 || !op.uniform_diag) return 0;
+  if (g.nn[0] < 32 || g.nn[1] < 8 || g.nzl < 8) return 0;
+  constexpr int YSB = 3;
+  static const int txmax_env = env_int("PDE_B200_P2_TXMAX", 94);
+  static const int zc_env = env_int("PDE_B200_P2_ZC", 64);
+  Post2Geom pg;
+  int txmax = txmax_env < 30 ? 30 : (txmax_env > P2_MAXT / 2 - 2 ? P2_MAXT / 2 - 2 : txmax_env);
+  pg.ntx = (g.nn[0] + txmax - 1) / txmax;
+  pg.tx = (g.nn[0] + pg.ntx - 1) / pg.ntx;
+  pg.tx += pg.tx & 1;
+  if (pg.tx > txmax) pg.tx = txmax - (txmax & 1);
+  pg.ntx = (g.nn[0] + pg.tx - 1) / pg.tx;
+  pg.ty = 2 * YSB;
+  pg.nty = (g.nn[1] + pg.ty - 1) / pg.ty;
+  pg.cw = pg.tx + 2;
+  pg.ra = pg.ty + 2;
+  pg.bx = pg.tx + 4;
+  pg.by = pg.ty + 4;
+  const int nt = ((2 * pg.cw + 31) / 32) * 32;
+  if (nt > P2_MAXT) PDE_FAIL("post2 tile exceeds the thread limit");
+  int zc = zc_env < 4 ? 4 : zc_env;
+  while (zc > 8 && (long long)pg.ntx * pg.nty * ((g.nzl + zc - 1) / zc) < 4LL * c->sm_count) zc /= 2;
+  pg.nzc = (g.nzl + zc - 1) / zc;
+  pg.zc = (g.nzl + pg.nzc - 1) / pg.nzc;
+  pg.nzc = (g.nzl + pg.zc - 1) / pg.zc;
+  pg.stage_elems = ((pg.bx * pg.by + 15) / 16) * 16;
+  pg.ring_elems = ((pg.cw * pg.ra + 15) / 16) * 16;
+  const long long items = (long long)pg.ntx * pg.nty * pg.nzc;
+  if (items > RED_MAX_BLOCKS) return 0;
+  const size_t smem = ((size_t)SW_STAGES * pg.stage_elems + 6 * (size_t)pg.ring_elems) * sizeof(double) +
+                      SW_STAGES * sizeof(uint64_t);
+  auto kern = k_post2<YSB>;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  CUtensorMap tm;
+  PDE_OK(field_tensor_map(x0, g, 1, pg.bx, pg.by, &tm));
+  Coef<1> C;
+  for (int k = 0; k < PDE_NOFF; ++k) C.c[k][0] = op.h_int[k];
+  Post2Args pa;
+  pa.b = b; pa.y = y;
+  pa.a0 = c2_0 * op.h_dinv_int[0];
+  pa.c1 = c1_1;
+  pa.a1 = c2_1 * op.h_dinv_int[0];
+  pa.do_reduce = dot_slot >= 0;
+  kern<<<(unsigned)items, nt, smem, c->stream>>>(tm, g, C, pa, pg, c->red, pa.do_reduce ? c->scal + dot_slot : nullptr);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  *handled = true;
   return 0;
 }
 

@@ -215,7 +215,7 @@ int make_grid(int dim, const int32_t n[3], const double L[3], int rank, int worl
     g->nzl = g->nzg;
   }
   g->total = g->plane * g->nzl;
-  g->comp_stride = g->plane * (g->nzl + 2);
+  g->comp_stride = g->plane * (g->nzl + 2 * PDE_NG);
   const int act1[] = {0, 1, 2}, act2[] = {0, 1, 2, 5, 6, 9, 10};
   if (dim == 1) { g->nk = 3; for (int k = 0; k < 3; ++k) g->kidx[k] = act1[k]; }
   else if (dim == 2) { g->nk = 7; for (int k = 0; k < 7; ++k) g->kidx[k] = act2[k]; }

@@ -84,6 +84,15 @@ if rank == 0:
     print(f"[mgpu] elasticity {en} x{world} gmg: von Mises rel-L2 {e_vm:.2e}, displacement rel-L2 {e_u:.2e}, "
           f"iters {st.iters_total} levels {st.levels}", flush=True)
     ok = ok and e_vm <= 1e-8 and e_u <= 1e-8 and st.converged == 1
+# ---- sizes that take the TMA sweep kernels and the temporally blocked smoother (2 halo planes): manufactured solutions
+for kind, mn, mL, faces in (("heat", [96, 40, 32 * world], [1.0, 0.5, 0.4 * world], {f: 0.0 for f in range(6)}),
+                            ("elasticity", [64, 16, 16 * world], [1.0, 0.25, 0.25 * world], {0: 0.0})):
+    mp = _lib.op_params(kind, 3, mn, mL, 1.0, 0.01, 121.15e9, 80.77e9, bc=_lib.make_bc(faces))
+    err, mst = _lib.op_manufactured(ctx, mp, _lib.make_opts(rtol=1e-11, precond="gmg"))
+    if rank == 0:
+        print(f"[mgpu] manufactured {kind} {mn} x{world}: rel-L2 {err:.2e} iters {mst['iters_total']} levels {mst['levels']} "
+              f"true relres {mst['true_relres']:.1e}", flush=True)
+        ok = ok and err <= 1e-8 and mst["converged"] == 1 and mst["levels"] > 1
 h_ms, h_bytes = _lib.halo_bench(ctx, 3, [512, 512, 64 * world], 1, reps=50)
 if rank == 0:
     print(f"[mgpu] halo exchange 513x513 plane: {h_ms * 1e3:.1f} us, {516 * 514 * 8 / (h_ms / 1e3) / 1e9:.0f} GB/s per direction",
