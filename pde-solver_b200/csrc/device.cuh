@@ -175,10 +175,13 @@ struct StencilArgs {
   int cheby = 0;                  // 1: one sweep; 2: first TWO sweeps from a zero guess, x = right-hand side
                                   // reduce_slot_xy with cheby: receives sum B.y (one value)
   int reduce_slot_xy = -1;        // scal slot receiving sum x.y (and +1: sum y.y) ; -1: none
+  int ghost_out = 0;              // slabs: also compute the ghost planes z = -1 and z = nzl of y (uniform-diagonal
+                                  // operators on the sweep kernel only; needs 2 halo planes of x, 1 of b; no reductions)
   int variant = 0;
 };
 
 int launch_stencil(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
+bool sweep_applicable(const Grid& g, int ncomp);
 // two restart Chebyshev sweeps in one pass (temporal blocking); *handled = false if not applicable
 int launch_post2(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* x0, const double* b,
                  double* y, double c2_0, double c1_1, double c2_1, int dot_slot, bool* handled);
@@ -201,8 +204,9 @@ int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& 
                        double s);
 int launch_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcc, int ncomp, const double* rf,
                     double* bcoarse);
+// ghost > 0: also correct `ghost` ghost planes on each side of the fine slab (coarse ghosts must be valid)
 int launch_prolong_add(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcf, int ncomp, const double* xc,
-                       double* xf);
+                       double* xf, int ghost = 0);
 // fields
 int launch_fill_ic(pde_ctx* c, const Grid& g, const BcDev& bc, double* u, double value, int apply_bc);
 int launch_fill_pattern(pde_ctx* c, const Grid& g, const BcDev& bc, int ncomp, double* x);

@@ -569,13 +569,15 @@ int launch_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcc
 template <int NC>
 __global__ void __launch_bounds__(128)
 k_prolong_add(const __grid_constant__ Grid gf, const __grid_constant__ Grid gc, const __grid_constant__ BcDev bcf,
-              const double* __restrict__ xc, double* __restrict__ xf) {
-  const long long rows = (long long)gf.nn[1] * gf.nzl;
+              const double* __restrict__ xc, double* __restrict__ xf, int ghost) {
+  const int nzr = gf.nzl + 2 * ghost;
+  const long long rows = (long long)gf.nn[1] * nzr;
   for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
        row += (long long)gridDim.x * blockDim.y) {
     const int iy = (int)(row % gf.nn[1]);
-    const int lz = (int)(row / gf.nn[1]);
+    const int lz = (int)(row / gf.nn[1]) - ghost;
     const int gz = lz + gf.z0;
+    if (gz < 0 || gz > gf.nzg - 1) continue;   // ghost plane beyond the domain end
     const long long fbase = (long long)gf.PX * iy + gf.plane * lz;
     const int py = gf.nc[1] > 0 ? (iy & 1) : 0;
     const int pz = gf.nc[2] > 0 ? (gz & 1) : 0;
@@ -599,9 +601,9 @@ k_prolong_add(const __grid_constant__ Grid gf, const __grid_constant__ Grid gc, 
 }
 
 int launch_prolong_add(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcf, int ncomp, const double* xc,
-                       double* xf) {
+                       double* xf, int ghost) {
   RowLaunch rl = row_launch(c, gf);
-  DISPATCH_NC(ncomp, (k_prolong_add<NC><<<rl.grid, rl.block, 0, c->stream>>>(gf, gc, bcf, xc, xf)));
+  DISPATCH_NC(ncomp, (k_prolong_add<NC><<<rl.grid, rl.block, 0, c->stream>>>(gf, gc, bcf, xc, xf, ghost)));
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

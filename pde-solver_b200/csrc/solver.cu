@@ -346,7 +346,7 @@ struct Cheby {
 // Chebyshev(Jacobi) smoothing.  dot_slot >= 0: the LAST sweep also leaves sum b.x_new in that scalar slot
 // (*dot_done tells whether a sweep could do it).
 static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double** oth, int sweeps, bool zero_guess,
-                  double ratio, int dot_slot = -1, bool* dot_done = nullptr) {
+                  double ratio, int dot_slot = -1, bool* dot_done = nullptr, bool halos_valid = false) {
   Cheby ch;
   ch.init(L.op.dev.gershgorin, ratio);
   int k0 = 0;
@@ -381,7 +381,7 @@ static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double*
     ch.coef(0, &c1a, &c2a);
     ch.coef(1, &c1b, &c2b);
     bool handled = false;
-    if (c->world > 1) {
+    if (c->world > 1 && !halos_valid) {
       PDE_OK(comm_halo_exchange(c, L.op.g, 1, *cur, PDE_NG));
       PDE_OK(comm_halo_exchange(c, L.op.g, 1, const_cast<double*>(b), 1));
     }
@@ -417,15 +417,24 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
   const int nl = (int)lv.size();
   std::vector<double*> cur(nl), oth(nl);
   for (int l = 0; l < nl; ++l) { cur[l] = lv[l]->xa.p; oth[l] = lv[l]->xb.p; }
+  // slabs, uniform-diagonal scalar levels: the iterate is exchanged ONCE per level with two halo planes; residual
+  // and prolongation are then computed on the ghost planes too, so neither the residual nor the corrected iterate
+  // needs an exchange of its own (3 exchanges per level and cycle instead of 6)
+  std::vector<char> lean(nl, 0);
+  for (int l = 0; l + 1 < nl; ++l)
+    lean[l] = c->world > 1 && nu == 2 && lv[l]->op.dev.uniform_diag && lv[l]->op.dev.ncomp == 1 && lv[l]->op.g.dim == 3 &&
+              lv[l]->op.g.nzl >= 8 && lv[l + 1]->op.g.nzl >= PDE_NG && sweep_applicable(lv[l]->op.g, 1) &&
+              !getenv("PDE_B200_NO_POST2") && !getenv("PDE_B200_NO_LEAN_HALO");
   for (int l = 0; l < nl - 1; ++l) {
     MGLevel& L = *lv[l];
     const double* b = l == 0 ? b0 : L.b.p;
-    PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, true, ratio));
+    PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, true, ratio));   // exchanges one halo plane of b (fused first sweeps)
     StencilArgs a;
     a.x = cur[l]; a.b = b; a.y = L.r.p; a.bscale = 1.0; a.ascale = -1.0;
-    if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, cur[l]));
+    a.ghost_out = lean[l];
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, cur[l], lean[l] ? PDE_NG : 1));
     PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
-    if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, L.r.p));
+    if (c->world > 1 && !lean[l]) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, L.r.p));
     PDE_OK(launch_restrict(c, L.op.g, lv[l + 1]->op.g, lv[l + 1]->op.bc, L.op.dev.ncomp, L.r.p, lv[l + 1]->b.p));
   }
   {
@@ -444,9 +453,10 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
   for (int l = nl - 2; l >= 0; --l) {
     MGLevel& L = *lv[l];
     const double* b = l == 0 ? b0 : L.b.p;
-    if (c->world > 1) PDE_OK(comm_halo_exchange(c, lv[l + 1]->op.g, L.op.dev.ncomp, cur[l + 1]));
-    PDE_OK(launch_prolong_add(c, L.op.g, lv[l + 1]->op.g, L.op.bc, L.op.dev.ncomp, cur[l + 1], cur[l]));
-    PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, false, ratio, l == 0 ? dot_slot : -1, l == 0 ? dot_done : nullptr));
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, lv[l + 1]->op.g, L.op.dev.ncomp, cur[l + 1], lean[l] ? PDE_NG : 1));
+    PDE_OK(launch_prolong_add(c, L.op.g, lv[l + 1]->op.g, L.op.bc, L.op.dev.ncomp, cur[l + 1], cur[l], lean[l] ? PDE_NG : 0));
+    PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, false, ratio, l == 0 ? dot_slot : -1, l == 0 ? dot_done : nullptr,
+                  lean[l] != 0));
   }
   *z_out = cur[0];
   return 0;

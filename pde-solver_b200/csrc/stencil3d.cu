@@ -34,6 +34,7 @@ struct SweepGeom {
   int ns;             // strips (of YS rows) per tile
   int stage_elems;    // doubles per stage (all components), multiple of 16
   int spec;           // 1: the last warp is a dedicated TMA producer (empty/full mbarriers, no CTA barrier)
+  int zlo, zhi;       // output plane range [zlo, zhi): [0, nzl), or [-1, nzl+1) when the ghost planes are computed too
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -191,8 +192,8 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
   const int ity = (item / sw.ntx) % sw.nty;
   const int izc = item / (sw.ntx * sw.nty);
   const int x0 = itx * sw.tx, y0 = ity * sw.ty;
-  const int za = izc * sw.zc;
-  const int zb = min(za + sw.zc, g.nzl);
+  const int za = sw.zlo + izc * sw.zc;
+  const int zb = min(za + sw.zc, sw.zhi);
   const int nplanes = zb - za + 2;  // planes za-1 .. zb
   const uint32_t stage_bytes = (uint32_t)(sw.bx * sw.by * NC * sizeof(double));
   const uint32_t bar0 = smem_u32(bars);
@@ -352,7 +353,8 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
     if (FIN) {
       const int gz = zout + g.z0;
       const bool ze0 = g.nc[2] > 0 && gz == 0, ze1 = g.nc[2] > 0 && gz == g.nzg - 1;
-      const bool zdir = !z_excl && ((ze0 && bc.on[4]) || (ze1 && bc.on[5]));
+      const bool zout_dom = gz < 0 || gz > g.nzg - 1;   // ghost plane beyond the domain end: nothing lives there
+      const bool zdir = zout_dom || (!z_excl && ((ze0 && bc.on[4]) || (ze1 && bc.on[5])));
       const double mz = zdir ? 0.0 : 1.0;
       unsigned todo = valid;
       const unsigned slow = zdir ? 0u : ((ze0 || ze1) ? freexy : slowxy);
@@ -730,9 +732,15 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   int zc = tu.zc < 2 ? 2 : tu.zc;
   // small grids (coarse multigrid levels): shorter z chunks so that the grid still covers the SMs
   while (zc > 4 && (long long)sw.ntx * sw.nty * ((g.nzl + zc - 1) / zc) < 4LL * c->sm_count) zc /= 2;
-  sw.nzc = (g.nzl + zc - 1) / zc;
-  sw.zc = (g.nzl + sw.nzc - 1) / sw.nzc;
-  sw.nzc = (g.nzl + sw.zc - 1) / sw.zc;
+  // ghost_out: also produce the two ghost planes next to the slab (needs two valid halo planes of x and one of b),
+  // so that the consumer (restriction) needs no halo exchange of the result
+  const int gout = (a.ghost_out && op.uniform_diag) ? 1 : 0;
+  sw.zlo = -gout;
+  sw.zhi = g.nzl + gout;
+  const int nzr = sw.zhi - sw.zlo;
+  sw.nzc = (nzr + zc - 1) / zc;
+  sw.zc = (nzr + sw.nzc - 1) / sw.nzc;
+  sw.nzc = (nzr + sw.zc - 1) / sw.zc;
   sw.stage_elems = ((sw.bx * sw.by * NC + 15) / 16) * 16;
   const long long items = (long long)sw.ntx * sw.nty * sw.nzc;
   if (items > RED_MAX_BLOCKS) PDE_FAIL("sweep grid exceeds the reduction buffer");
@@ -824,14 +832,22 @@ int launch_post2(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, co
   return 0;
 }
 
+// does the TMA plane-sweep kernel take this grid?  (callers that rely on its ghost-plane outputs must ask)
+bool sweep_applicable(const Grid& g, int ncomp) {
+  static const int off = env_int("PDE_B200_NO_SWEEP", 0);
+  if (off) return false;
+  if (g.dim != 3 || g.nk != PDE_NOFF) return false;
+  if (ncomp != 1 && ncomp != 3) return false;
+  // small grids (coarse multigrid levels) stay on the generic kernel: they are launch-latency bound
+  if (g.nn[0] < 32 || g.nn[1] < 8 || g.nzl < 4) return false;
+  if ((long long)g.nn[0] * g.nn[1] * g.nzl < 4096) return false;
+  return true;
+}
+
 int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a,
                         bool* handled) {
   *handled = false;
-  if (g.dim != 3 || g.nk != PDE_NOFF) return 0;
-  if (env_int("PDE_B200_NO_SWEEP", 0)) return 0;
-  // small grids (coarse multigrid levels) stay on the generic kernel: they are launch-latency bound
-  if (g.nn[0] < 32 || g.nn[1] < 8 || g.nzl < 4) return 0;
-  if ((long long)g.nn[0] * g.nn[1] * g.nzl < 4096) return 0;
+  if (!sweep_applicable(g, op.ncomp)) return 0;
   const int ys = sweep_tune().ys;
   *handled = true;
 #define SWEEP_DISPATCH_S(NC_, YS_, SP_)                                                   \
