@@ -436,8 +436,17 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
 //   strip of YSB+1 rows in stage A and YSB rows in stage B; TY = 2*YSB rows of output per tile.
 //   Input planes za-2 .. zb+1 are needed for outputs za .. zb-1: fields carry PDE_NG = 2 ghost planes.
 // ----------------------------------------------------------------------------------------------------
-#define P2_MAXT 192
-#define P2_MINB 2
+// tuned on B200 by A/B builds (heat 512^3 step, ms): YSB/threads/minBlocks 3/192/2 68.4, 4/192/2 66.7, 4/128/3 66.4,
+// 2/192/3 71.5, 5/192/2 76.6, 6/192/1 72.9
+#ifndef P2_MAXT
+#define P2_MAXT 128
+#endif
+#ifndef P2_MINB
+#define P2_MINB 3
+#endif
+#ifndef P2_YSB
+#define P2_YSB 4
+#endif
 
 struct Post2Geom {
   int tx, ty;          // output tile
@@ -780,7 +789,7 @@ int launch_post2(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, co
   if (env_int("PDE_B200_NO_POST2", 0)) return 0;
   if (g.dim != 3 || g.nk != PDE_NOFF || op.ncomp != 1 || !op.uniform_diag) return 0;
   if (g.nn[0] < 32 || g.nn[1] < 8 || g.nzl < 8) return 0;
-  constexpr int YSB = 3;
+  constexpr int YSB = P2_YSB;
   static const int txmax_env = env_int("PDE_B200_P2_TXMAX", 94);
   static const int zc_env = env_int("PDE_B200_P2_ZC", 64);
   Post2Geom pg;
