@@ -372,10 +372,72 @@ int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op
   return 0;
 }
 
+// GMG-PCG variants of the two vector updates: no class-dependent Jacobi diagonal is involved, so they run flat
+// over the padded storage with 16-byte accesses (pads and ghost planes hold zeros in p, q, z and stay zero).
+__global__ void __launch_bounds__(256)
+k_cg_update_flat(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                 const double* __restrict__ q, long long n, int ncomp, long long cs, const double* __restrict__ scal,
+                 int s_rho, int s_pap, ReduceBuf red, double* out_rho_new) {
+  const double pap = scal[s_pap], rho = scal[s_rho];
+  const double alpha = pap > 0.0 ? rho / pap : 0.0;
+  const long long n2 = n >> 1;
+  double rr = 0.0;
+  for (int cidx = 0; cidx < ncomp; ++cidx) {
+    double2* x2 = reinterpret_cast<double2*>(x + cidx * cs);
+    double2* r2 = reinterpret_cast<double2*>(r + cidx * cs);
+    const double2* p2 = reinterpret_cast<const double2*>(p + cidx * cs);
+    const double2* q2 = reinterpret_cast<const double2*>(q + cidx * cs);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+      const double2 pv = p2[i], qv = q2[i];
+      double2 xv = x2[i], rv = r2[i];
+      xv.x = fma(alpha, pv.x, xv.x);
+      xv.y = fma(alpha, pv.y, xv.y);
+      rv.x = fma(-alpha, qv.x, rv.x);
+      rv.y = fma(-alpha, qv.y, rv.y);
+      x2[i] = xv;
+      r2[i] = rv;
+      rr = fma(rv.x, rv.x, rr);
+      rr = fma(rv.y, rv.y, rr);
+    }
+  }
+  // slots (rho_new, rr): the preconditioned product is filled in later by the V-cycle's last sweep
+  double v[2] = {0.0, rr};
+  block_reduce_finalize<2>(v, red, out_rho_new);
+}
+
+__global__ void __launch_bounds__(256)
+k_cg_pupdate_flat(double* __restrict__ p, const double* __restrict__ z, long long n, int ncomp, long long cs,
+                  const double* __restrict__ scal, int s_rho, int s_rho_new, int first) {
+  double beta = 0.0;
+  if (!first) {
+    const double rho = scal[s_rho];
+    beta = rho > 0.0 ? scal[s_rho_new] / rho : 0.0;
+  }
+  const long long n2 = n >> 1;
+  for (int cidx = 0; cidx < ncomp; ++cidx) {
+    double2* p2 = reinterpret_cast<double2*>(p + cidx * cs);
+    const double2* z2 = reinterpret_cast<const double2*>(z + cidx * cs);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+      const double2 zv = z2[i];
+      double2 pv = first ? make_double2(0.0, 0.0) : p2[i];
+      pv.x = fma(beta, pv.x, zv.x);
+      pv.y = fma(beta, pv.y, zv.y);
+      p2[i] = pv;
+    }
+  }
+}
+
 int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, double* r, const double* p,
                      const double* q, int slot_rho, int slot_pap, int slot_rho_new, int slot_rr, int jacobi) {
-  (void)jacobi;
   if (slot_rr != slot_rho_new + 1) PDE_FAIL("cg_update needs adjacent (rho_new, rr) slots");
+  if (!jacobi) {
+    int blocks = flat_blocks(c, g.total / 2, 256 * 2);
+    k_cg_update_flat<<<blocks, 256, 0, c->stream>>>(x, r, p, q, g.total, op.ncomp, g.comp_stride, c->scal, slot_rho,
+                                                    slot_pap, c->red, c->scal + slot_rho_new);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   RowLaunch rl = row_launch(c, g);
   DISPATCH_NC(op.ncomp, (k_cg_update<NC><<<rl.grid, rl.block, 0, c->stream>>>(
                             g, op.dinv, x, r, p, q, c->scal, slot_rho, slot_pap, c->red, c->scal + slot_rho_new,
@@ -387,6 +449,14 @@ int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, doub
 
 int launch_cg_pupdate(pde_ctx* c, const Grid& g, const OpDev& op, double* p, const double* r_or_z, int slot_rho,
                       int slot_rho_new, int first, int jacobi) {
+  if (!jacobi) {
+    int blocks = flat_blocks(c, g.total / 2, 256 * 2);
+    k_cg_pupdate_flat<<<blocks, 256, 0, c->stream>>>(p, r_or_z, g.total, op.ncomp, g.comp_stride, c->scal, slot_rho,
+                                                     slot_rho_new, first);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   RowLaunch rl = row_launch(c, g);
   DISPATCH_NC(op.ncomp, (k_cg_pupdate<NC><<<rl.grid, rl.block, 0, c->stream>>>(
                             g, op.dinv, p, r_or_z, c->scal, slot_rho, slot_rho_new, first, jacobi)));
