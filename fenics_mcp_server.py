@@ -13,10 +13,10 @@ Reference boundary (file:line under /root/reference/fenics_mcp_server.py):
 The orchestrator launches this file as a stdio child (multi_agent_orchestrator.py:27, 70-78); stdout is
 the JSON-RPC channel, so nothing here or in the CUDA library prints to it.
 
-In scope: the six Cartesian tools above (box geometry, uniform diffusivity).  The curvilinear heat
-tools (:2044-2119, 2220-2520) and the cylinder / composite-core branches of solve_heat_3D are
-registered with their reference signatures so tool lookups behave (dispatcher_agent.py:149-184) and
-raise a clear error: they are outside this build's hot path.
+All eleven solve tools run on the GPU: the six Cartesian ones (box geometry, uniform diffusivity) and the five
+curvilinear heat tools (:2044-2119, 2220-2520; same loop with one scalar weight).  The cylinder
+(mshr) and composite-core branches of solve_heat_3D (:512-572) raise a clear error: unstructured mesh / DG0
+coefficient, outside this build (n4).
 
 Solver knobs the reference does not have come from the environment so existing callers are
 unaffected: PDE_B200_RTOL (default 1e-10), PDE_B200_PRECOND (auto|gmg|jacobi),
@@ -74,12 +74,6 @@ def _save(field: TimeSeriesField, data_dir: str, stem: str, tag: Optional[str] =
     with open(filepath, "wb") as f:
         pickle.dump(field, f, protocol=pickle.HIGHEST_PROTOCOL)
     return SolveResult(data_file=str(filepath), dim=field.dim, meta=field.meta)
-
-
-def _out_of_scope(tool: str, where: str):
-    raise NotImplementedError(
-        f"{tool}: curvilinear / unstructured heat solves (reference {where}) are outside the structured-mesh "
-        "Cartesian hot path of the B200 build; run this tool with the reference FEniCS server")
 
 
 # ─────────────────────────────── heat (Cartesian, in scope) ───────────────────────────────
@@ -241,7 +235,7 @@ def solve_elasticity_3D_static(
     return _save(field, data_dir, f"elasticity_3d_{quantity}")
 
 
-# ─────────────────── curvilinear heat tools: registered, outside the hot path ───────────────────
+# ─────────────────── curvilinear heat tools (reference :2044-2119, 2220-2520) ───────────────────
 @mcp.tool()
 def solve_heat_3D_spherical(
     r_inner: float = 0.1, r_outer: float = 1.0, nr: int = 20, ntheta: int = 20, nphi: int = 20,
@@ -249,8 +243,13 @@ def solve_heat_3D_spherical(
     num_steps: int = 50, data_dir: str = "data", steady: bool = False, source_type: str = "none",
     source_value: float = 0.0, initial_type: str = "constant", initial_amplitude: float = 1.0,
 ) -> SolveResult:
-    """3D heat equation in spherical coordinates (r-theta-phi).  Not part of this build."""
-    _out_of_scope("solve_heat_3D_spherical", ":1326-1464, 2044-2119")
+    """3D heat equation in spherical coordinates (r, theta, phi) on [r_inner, r_outer] x [0, pi] x [0, 2 pi]."""
+    field = _p._solve_heat_3d_spherical_raw(
+        r_inner=r_inner, r_outer=r_outer, nr=nr, ntheta=ntheta, nphi=nphi, diffusivity=diffusivity,
+        T_boundary=T_boundary, T_initial=T_initial, dt=dt, num_steps=num_steps, steady=steady, source_type=source_type,
+        source_value=source_value, initial_type=initial_type, initial_amplitude=initial_amplitude,
+        rtol=_knobs()["rtol"])
+    return _save(field, data_dir, "heat_3d_spherical")
 
 
 @mcp.tool()
@@ -260,8 +259,13 @@ def solve_heat_1D_cylindrical(
     steady: bool = False, source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
     initial_amplitude: float = 1.0,
 ) -> SolveResult:
-    """1D radial heat equation in cylindrical coordinates.  Not part of this build."""
-    _out_of_scope("solve_heat_1D_cylindrical", ":769-920, 2220-2292")
+    """1D radial heat equation in cylindrical coordinates on (r_inner, r_outer)."""
+    field = _p._solve_heat_1d_cylindrical_raw(
+        r_inner=r_inner, r_outer=r_outer, nr=nr, diffusivity=diffusivity, T_inner=T_inner, T_outer=T_outer,
+        T_initial=T_initial, dt=dt, num_steps=num_steps, steady=steady, source_type=source_type,
+        source_value=source_value, initial_type=initial_type, initial_amplitude=initial_amplitude,
+        rtol=_knobs()["rtol"])
+    return _save(field, data_dir, "heat_1d_cylindrical")
 
 
 @mcp.tool()
@@ -271,8 +275,13 @@ def solve_heat_1D_spherical(
     steady: bool = False, source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
     initial_amplitude: float = 1.0,
 ) -> SolveResult:
-    """1D radial heat equation in spherical coordinates.  Not part of this build."""
-    _out_of_scope("solve_heat_1D_spherical", ":926-1057, 2295-2367")
+    """1D radial heat equation in spherical coordinates on (r_inner, r_outer)."""
+    field = _p._solve_heat_1d_spherical_raw(
+        r_inner=r_inner, r_outer=r_outer, nr=nr, diffusivity=diffusivity, T_inner=T_inner, T_outer=T_outer,
+        T_initial=T_initial, dt=dt, num_steps=num_steps, steady=steady, source_type=source_type,
+        source_value=source_value, initial_type=initial_type, initial_amplitude=initial_amplitude,
+        rtol=_knobs()["rtol"])
+    return _save(field, data_dir, "heat_1d_spherical")
 
 
 @mcp.tool()
@@ -282,8 +291,13 @@ def solve_heat_2D_cylindrical(
     num_steps: int = 50, data_dir: str = "data", steady: bool = False, source_type: str = "none",
     source_value: float = 0.0, initial_type: str = "constant", initial_amplitude: float = 1.0,
 ) -> SolveResult:
-    """2D axisymmetric heat equation in cylindrical coordinates (r-z).  Not part of this build."""
-    _out_of_scope("solve_heat_2D_cylindrical", ":1063-1185, 2370-2445")
+    """2D axisymmetric heat equation in cylindrical coordinates (r, z)."""
+    field = _p._solve_heat_2d_cylindrical_raw(
+        r_inner=r_inner, r_outer=r_outer, z_length=z_length, nr=nr, nz=nz, diffusivity=diffusivity,
+        T_boundary=T_boundary, T_initial=T_initial, dt=dt, num_steps=num_steps, steady=steady, source_type=source_type,
+        source_value=source_value, initial_type=initial_type, initial_amplitude=initial_amplitude,
+        rtol=_knobs()["rtol"])
+    return _save(field, data_dir, "heat_2d_cylindrical")
 
 
 @mcp.tool()
@@ -293,8 +307,13 @@ def solve_heat_2D_spherical(
     data_dir: str = "data", steady: bool = False, source_type: str = "none", source_value: float = 0.0,
     initial_type: str = "constant", initial_amplitude: float = 1.0,
 ) -> SolveResult:
-    """2D axisymmetric heat equation in spherical coordinates (r-theta).  Not part of this build."""
-    _out_of_scope("solve_heat_2D_spherical", ":1191-1320, 2448-2520")
+    """2D axisymmetric heat equation in spherical coordinates (r, theta)."""
+    field = _p._solve_heat_2d_spherical_raw(
+        r_inner=r_inner, r_outer=r_outer, nr=nr, ntheta=ntheta, diffusivity=diffusivity, T_boundary=T_boundary,
+        T_initial=T_initial, dt=dt, num_steps=num_steps, steady=steady, source_type=source_type,
+        source_value=source_value, initial_type=initial_type, initial_amplitude=initial_amplitude,
+        rtol=_knobs()["rtol"])
+    return _save(field, data_dir, "heat_2d_spherical")
 
 
 # ─────────────────────────────── plot tools (consumers of the .pkl) ───────────────────────────────

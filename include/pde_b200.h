@@ -65,6 +65,10 @@ int pde_halo_bench(pde_ctx* ctx, int dim, const int32_t n[3], int ncomp, int rep
 int pde_mesh_counts(int dim, const int32_t n[3], int64_t* nverts, int64_t* ncells);
 int pde_mesh_coords(pde_ctx* ctx, int dim, const int32_t n[3], const double L[3],
                     double* coords /* [nverts][dim] */);
+/* same generators on [lo, hi] (IntervalMesh(n,a,b) :804,960; RectangleMesh(Point(a,..),..) :1096,1223;
+ * BoxMesh(Point(a,..),..) :1360) - the coordinate spaces of the curvilinear tools */
+int pde_mesh_coords_box(pde_ctx* ctx, int dim, const int32_t n[3], const double lo[3], const double hi[3],
+                        double* coords /* [nverts][dim] */);
 /* sorted=0: generation order of each cell's vertices; sorted=1: after mesh.order() */
 int pde_mesh_cells(pde_ctx* ctx, int dim, const int32_t n[3], int sorted,
                    int32_t* cells /* [ncells][dim+1] */);
@@ -146,6 +150,30 @@ int pde_heat_step(pde_heat_state* s, int nsteps, pde_stats* st);
 int pde_heat_get_state(pde_heat_state* s, double* u_host /* [local nverts] */);
 int64_t pde_heat_local_nverts(pde_heat_state* s);
 int pde_heat_close(pde_heat_state* s);
+
+/* ---- curvilinear heat tools: _solve_heat_{1d,2d}_cylindrical_raw, _solve_heat_{1d,2d,3d}_spherical_raw :769-1464 ----
+ * Same backward-Euler / steady P1 solve on the coordinate-space mesh [lo,hi] with ONE scalar weight in every term:
+ *   a = w u v dx + dt k w grad(u).grad(v) dx,  L = w u_n v dx + dt w f v dx,
+ *   w = x0^weight_rpow * (weight_sin_axis1 ? sin(x1) : 1), an Expression of degree weight_degree (1 or 2).
+ * The initial state is the constant T_initial (every initial_type of these tools falls back to it). */
+typedef struct pde_wheat_params {
+  int32_t dim;
+  int32_t n[3];
+  double lo[3], hi[3];
+  int32_t weight_rpow;        /* 1: w ~ r (cylindrical), 2: w ~ r^2 (spherical) */
+  int32_t weight_sin_axis1;   /* 1: times sin(x[1]) (2D/3D spherical) */
+  int32_t weight_degree;      /* degree of the weight Expression: 1 or 2 */
+  int32_t steady;
+  double diffusivity;
+  double dt;
+  int32_t num_steps;
+  int32_t snapshot_stride;
+  double source_value;
+  double T_initial;
+  pde_bc bc;
+} pde_wheat_params;
+int pde_wheat_solve(pde_ctx* ctx, const pde_wheat_params* p, const pde_solver_opts* o,
+                    double* values_out /* [nsnap][nverts] */, double* times_out, pde_stats* st);
 
 /* ---- elasticity: _solve_elasticity_{1,2,3}d_static :1470-1587, 1593-1743, 1749-1892 ---- */
 typedef struct pde_elast_params {

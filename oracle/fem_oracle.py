@@ -531,3 +531,162 @@ def canonical_order(coords: np.ndarray, L: Sequence[float], n: Sequence[int]) ->
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
     nb = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / nb) if nb > 0 else float(np.linalg.norm(a - b))
+
+
+# --------------------------------------------------------------------------------------
+# Curvilinear heat tools (reference :769-1464): the same P1 backward-Euler loop with ONE scalar weight w(x) in
+# every term,  a = w u v dx + dt k w grad(u).grad(v) dx,  L = w u_n v dx + dt w f v dx,  where w is an
+# Expression of degree 1 (x[0]) or 2 (x[0]^2, x[0]^2 sin(x[1])).  FFC interpolates a degree-p Expression into
+# the P_p element on every cell and integrates the resulting polynomial exactly, which is what is restated.
+# --------------------------------------------------------------------------------------
+
+def _mono(d, alpha):
+    """Integral of prod(lambda_k^alpha_k) over the unit-volume d-simplex: d! prod(alpha!) / (d + |alpha|)!"""
+    f = math.factorial
+    return f(d) * np.prod([f(a) for a in alpha]) / f(d + sum(alpha))
+
+
+def _weight_basis_integrals(d, degree):
+    """Per weight basis function k: (Ws[k] = int psi_k, Wl[k][i] = int psi_k lam_i, Wm[k][i][j] = int psi_k lam_i lam_j),
+    all for a unit-volume simplex; weight basis = P1 (vertices) or P2 (vertices, then edges a<b)."""
+    nv = d + 1
+
+    def e(*idx):
+        a = [0] * nv
+        for i in idx:
+            a[i] += 1
+        return a
+
+    polys = []   # each psi as a list of (coef, exponent-vector)
+    for v in range(nv):
+        if degree == 1:
+            polys.append([(1.0, e(v))])
+        else:
+            polys.append([(2.0, e(v, v)), (-1.0, e(v))])
+    if degree == 2:
+        for a, b in itertools.combinations(range(nv), 2):
+            polys.append([(4.0, e(a, b))])
+    nk = len(polys)
+    Ws, Wl, Wm = np.zeros(nk), np.zeros((nk, nv)), np.zeros((nk, nv, nv))
+    for k, poly in enumerate(polys):
+        for cf, ex in poly:
+            Ws[k] += cf * _mono(d, ex)
+            for i in range(nv):
+                exi = list(ex)
+                exi[i] += 1
+                Wl[k, i] += cf * _mono(d, exi)
+                for j in range(nv):
+                    exij = list(exi)
+                    exij[j] += 1
+                    Wm[k, i, j] += cf * _mono(d, exij)
+    return Ws, Wl, Wm
+
+
+def assemble_weighted(mesh: Mesh, wfun: Callable[[np.ndarray], np.ndarray], degree: int):
+    """(Kw, Mw, mw): int I_p(w) grad(phi_i).grad(phi_j), int I_p(w) phi_i phi_j, int I_p(w) phi_i."""
+    d = mesh.dim
+    vol, G = _gradients(mesh)
+    c = mesh.cells.astype(np.int64)
+    X = mesh.coords[c]
+    nv = d + 1
+    Ws, Wl, Wm = _weight_basis_integrals(d, degree)
+    wk = [wfun(X[:, a, :]) for a in range(nv)]
+    if degree == 2:
+        wk += [wfun(0.5 * (X[:, a, :] + X[:, b, :])) for a, b in itertools.combinations(range(nv), 2)]
+    wk = np.stack(wk, axis=1)                                  # (ncells, nk)
+    wbar = wk @ Ws                                             # int I(w) / vol
+    rows, cols, kv, mv = [], [], [], []
+    load = np.zeros(mesh.nv)
+    for i in range(nv):
+        np.add.at(load, c[:, i], vol * (wk @ Wl[:, i]))
+        for j in range(nv):
+            rows.append(c[:, i])
+            cols.append(c[:, j])
+            kv.append(vol * wbar * np.einsum("ck,ck->c", G[:, i, :], G[:, j, :]))
+            mv.append(vol * (wk @ Wm[:, i, j]))
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    return (_assemble(rows, cols, np.concatenate(kv), mesh.nv), _assemble(rows, cols, np.concatenate(mv), mesh.nv),
+            load)
+
+
+CURVILINEAR = {
+    # kind: (dim, weight degree, weight function of the mesh coordinates)
+    "1d_cylindrical": (1, 1, lambda x: x[:, 0]),
+    "1d_spherical": (1, 2, lambda x: x[:, 0] * x[:, 0]),
+    "2d_cylindrical": (2, 1, lambda x: x[:, 0]),
+    "2d_spherical": (2, 2, lambda x: x[:, 0] * x[:, 0] * np.sin(x[:, 1])),
+    "3d_spherical": (3, 2, lambda x: x[:, 0] * x[:, 0] * np.sin(x[:, 1])),
+}
+
+
+def curvilinear_mesh(kind, r_inner, r_outer, n, z_length=None):
+    """IntervalMesh(nr, r_inner, r_outer) :804,960 / RectangleMesh(Point(r_inner,0), Point(r_outer, z_length|pi))
+    :1096,1223 / BoxMesh(Point(r_inner,0,0), Point(r_outer, pi, 2pi)) :1360-1364."""
+    if kind.startswith("1d"):
+        return interval_mesh(n[0], r_inner, r_outer)
+    if kind == "2d_cylindrical":
+        return rectangle_mesh(r_inner, 0.0, r_outer, z_length, n[0], n[1])
+    if kind == "2d_spherical":
+        return rectangle_mesh(r_inner, 0.0, r_outer, np.pi, n[0], n[1])
+    return box_mesh((r_inner, 0.0, 0.0), (r_outer, np.pi, 2.0 * np.pi), n[0], n[1], n[2])
+
+
+def curvilinear_coords(kind, X):
+    """Output embedding of the dof coordinates (:918, 1040, 1167, 1298-1303, 1439-1444)."""
+    out = np.zeros((X.shape[0], 3))
+    if kind.startswith("1d"):
+        out[:, 0] = X[:, 0]
+    elif kind == "2d_cylindrical":
+        out[:, 0], out[:, 2] = X[:, 0], X[:, 1]
+    elif kind == "2d_spherical":
+        out[:, 0] = X[:, 0] * np.sin(X[:, 1])
+        out[:, 2] = X[:, 0] * np.cos(X[:, 1])
+    else:
+        out[:, 0] = X[:, 0] * np.sin(X[:, 1]) * np.cos(X[:, 2])
+        out[:, 1] = X[:, 0] * np.sin(X[:, 1]) * np.sin(X[:, 2])
+        out[:, 2] = X[:, 0] * np.cos(X[:, 1])
+    return out
+
+
+def solve_heat_curvilinear(kind: str, r_inner: float, r_outer: float, n: Sequence[int], diffusivity: float,
+                           T_initial: float = 20.0, dt: float = 0.01, num_steps: int = 50, steady: bool = False,
+                           source_type: str = "none", source_value: float = 0.0, T_inner: float = 100.0,
+                           T_outer: float = 20.0, T_boundary: float = 20.0, z_length: float = 2.0) -> Field:
+    """_solve_heat_{1d_cylindrical,1d_spherical,2d_cylindrical,2d_spherical,3d_spherical}_raw restated."""
+    dim, degree, wfun = CURVILINEAR[kind]
+    mesh = curvilinear_mesh(kind, r_inner, r_outer, n, z_length)
+    Kw, Mw, mw = assemble_weighted(mesh, wfun, degree)
+    if dim == 1:
+        bcs = []
+        if r_inner > 1e-10:
+            bcs.append((dirichlet_dofs(mesh, lambda x, ob: ob & near(x[:, 0], r_inner)), T_inner))
+        bcs.append((dirichlet_dofs(mesh, lambda x, ob: ob & near(x[:, 0], r_outer)), T_outer))
+    else:
+        bcs = [(dirichlet_dofs(mesh, lambda x, ob: ob), T_boundary)]
+    bc_dofs, bc_vals = _merge_bcs(bcs, mesh.nv)
+    f = float(source_value) if source_type == "constant" else 0.0
+    kappa = float(diffusivity)
+    snaps, times = [], []
+    if steady:
+        A, b = apply_bc_rowwise((kappa * Kw).tocsr(), f * mw, bc_dofs, bc_vals)
+        snaps.append(lu_solve(A, b))
+        times.append(0.0)
+    else:
+        u = np.full(mesh.nv, float(T_initial))       # every initial_type falls back to the constant (:893-896)
+        u[bc_dofs] = bc_vals
+        snaps.append(u.copy())
+        times.append(0.0)
+        A, _ = apply_bc_rowwise((Mw + (dt * kappa) * Kw).tocsr(), np.zeros(mesh.nv), bc_dofs, bc_vals)
+        lu = _ScaledLU(A.tocsr())
+        for step in range(num_steps):
+            b = Mw @ u + (dt * f) * mw
+            b[bc_dofs] = bc_vals
+            u = lu.solve(b)
+            snaps.append(u.copy())
+            times.append((step + 1) * dt)
+    vals = np.array(snaps)
+    coords = curvilinear_coords(kind, mesh.coords)
+    if dim == 1:                                      # the 1D tools sort by r (:872-874)
+        order = np.argsort(mesh.coords[:, 0], kind="stable")
+        coords, vals = coords[order], vals[:, order]
+    return Field(coords=coords, values=vals, times=np.array(times), dim=dim, meta={"kind": kind})

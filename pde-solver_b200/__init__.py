@@ -9,6 +9,8 @@ from . import _lib  # noqa: F401
 from .solvers import (  # noqa: F401
     _solve_heat_1d_raw, _solve_heat_2d_raw, _solve_heat_3d_raw,
     _solve_elasticity_1d_static, _solve_elasticity_2d_static, _solve_elasticity_3d_static,
+    _solve_heat_1d_cylindrical_raw, _solve_heat_1d_spherical_raw, _solve_heat_2d_cylindrical_raw,
+    _solve_heat_2d_spherical_raw, _solve_heat_3d_spherical_raw,
     last_stats,
 )
 from . import mesh  # noqa: F401

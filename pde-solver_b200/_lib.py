@@ -47,6 +47,13 @@ class ElastParams(C.Structure):
                 ("plane_stress", C.c_int32), ("area", C.c_double)]
 
 
+class WheatParams(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("n", C.c_int32 * 3), ("lo", C.c_double * 3), ("hi", C.c_double * 3),
+                ("weight_rpow", C.c_int32), ("weight_sin_axis1", C.c_int32), ("weight_degree", C.c_int32),
+                ("steady", C.c_int32), ("diffusivity", C.c_double), ("dt", C.c_double), ("num_steps", C.c_int32),
+                ("snapshot_stride", C.c_int32), ("source_value", C.c_double), ("T_initial", C.c_double), ("bc", Bc)]
+
+
 class OpParams(C.Structure):
     _fields_ = [("kind", C.c_int32), ("dim", C.c_int32), ("n", C.c_int32 * 3), ("L", C.c_double * 3),
                 ("alpha", C.c_double), ("beta", C.c_double), ("lam", C.c_double), ("mu", C.c_double),
@@ -83,7 +90,8 @@ def lib():
                      "pde_mesh_cells", "pde_dofmap_cells", "pde_boundary_mask", "pde_heat_solve",
                      "pde_heat_open", "pde_heat_set_state", "pde_heat_step", "pde_heat_get_state",
                      "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench",
-                     "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition", "pde_op_manufactured", "pde_halo_bench"):
+                     "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition", "pde_op_manufactured", "pde_halo_bench", "pde_wheat_solve",
+                     "pde_mesh_coords_box"):
             getattr(L, name).restype = C.c_int
         _lib = L
     return _lib

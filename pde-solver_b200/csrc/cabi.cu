@@ -138,6 +138,18 @@ extern "C" int pde_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const do
   return d2h(c, coords, d.p, sizeof(double) * nv * dim);
 }
 
+extern "C" int pde_mesh_coords_box(pde_ctx* c, int dim, const int32_t n[3], const double lo[3], const double hi[3],
+                                   double* coords) {
+  if (!c) PDE_FAIL("null context");
+  CUDA_OK(cudaSetDevice(c->device));
+  int64_t nv, nc;
+  PDE_OK(pde_mesh_counts(dim, n, &nv, &nc));
+  DevMem d;
+  PDE_OK(d.alloc(sizeof(double) * nv * dim));
+  PDE_OK(launch_mesh_coords_box(c, dim, n, lo, hi, (double*)d.p));
+  return d2h(c, coords, d.p, sizeof(double) * nv * dim);
+}
+
 extern "C" int pde_dofmap_cells(pde_ctx* c, int dim, const int32_t n[3], int ncomp, int layout, int32_t* out) {
   if (!c) PDE_FAIL("null context");
   if (ncomp < 1 || ncomp > 3) PDE_FAIL("ncomp must be 1..3");

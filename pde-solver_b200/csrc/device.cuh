@@ -224,6 +224,7 @@ int launch_dense_gather(pde_ctx* c, int n, const long long* idx, const double* b
 int launch_dense_solve_owned(pde_ctx* c, int n, const double* Ainv, const long long* idx, const double* bglob, double* x);
 // mesh
 int launch_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* out);
+int launch_mesh_coords_box(pde_ctx* c, int dim, const int32_t n[3], const double lo[3], const double hi[3], double* out);
 int launch_mesh_cells(pde_ctx* c, int dim, const int32_t n[3], int sorted, int ncomp, int layout, int32_t* out);
 int launch_bc_mask(pde_ctx* c, const Grid& g, const BcDev& bc, uint8_t* mask, double* vals);
 

@@ -1043,34 +1043,44 @@ int launch_p2_load(pde_ctx* c, const Grid& g, const SimplexGeom& sg, double amp,
 // ----------------------------------------------------------------------------------------------
 // mesh / dof-map / boundary-set generation (bit-exact integer + FP64 coordinate expressions)
 // ----------------------------------------------------------------------------------------------
+struct Box3 {
+  double lo[3], hi[3];
+};
+
 __global__ void __launch_bounds__(256)
-k_mesh_coords(int dim, int n0, int n1, int n2, double L0, double L1, double L2, long long nv, double* __restrict__ out) {
+k_mesh_coords(int dim, int n0, int n1, int n2, const __grid_constant__ Box3 bx, long long nv, double* __restrict__ out) {
   const long long nn0 = n0 + 1, nn1 = dim >= 2 ? n1 + 1 : 1;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += (long long)gridDim.x * blockDim.x) {
     const long long ix = v % nn0, iy = (v / nn0) % nn1, iz = v / (nn0 * nn1);
     const long long ii[3] = {ix, iy, iz};
-    const double L[3] = {L0, L1, L2};
     const int n[3] = {n0, n1, n2};
     for (int k = 0; k < dim; ++k) {
+      const double a = bx.lo[k], b = bx.hi[k];
       double xk;
-      if (dim == 3)  // BoxMesh: a + (i*(b-a))/n   (a = 0)
-        xk = __dadd_rn(0.0, __ddiv_rn(__dmul_rn((double)ii[k], __dsub_rn(L[k], 0.0)), (double)n[k]));
+      if (dim == 3)  // BoxMesh: a + (i*(b-a))/n
+        xk = __dadd_rn(a, __ddiv_rn(__dmul_rn((double)ii[k], __dsub_rn(b, a)), (double)n[k]));
       else           // IntervalMesh / RectangleMesh: a + ((b-a)/n)*i
-        xk = __dadd_rn(0.0, __dmul_rn(__ddiv_rn(__dsub_rn(L[k], 0.0), (double)n[k]), (double)ii[k]));
+        xk = __dadd_rn(a, __dmul_rn(__ddiv_rn(__dsub_rn(b, a), (double)n[k]), (double)ii[k]));
       out[v * dim + k] = xk;
     }
   }
 }
 
-int launch_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* out) {
+int launch_mesh_coords_box(pde_ctx* c, int dim, const int32_t n[3], const double lo[3], const double hi[3], double* out) {
   int64_t nv, ncell;
   PDE_OK(pde_mesh_counts(dim, n, &nv, &ncell));
+  Box3 bx;
+  for (int k = 0; k < 3; ++k) { bx.lo[k] = k < dim ? lo[k] : 0.0; bx.hi[k] = k < dim ? hi[k] : 0.0; }
   int blocks = flat_blocks(c, nv, 256);
-  k_mesh_coords<<<blocks, 256, 0, c->stream>>>(dim, n[0], dim > 1 ? n[1] : 0, dim > 2 ? n[2] : 0, L[0],
-                                                dim > 1 ? L[1] : 0.0, dim > 2 ? L[2] : 0.0, nv, out);
+  k_mesh_coords<<<blocks, 256, 0, c->stream>>>(dim, n[0], dim > 1 ? n[1] : 0, dim > 2 ? n[2] : 0, bx, nv, out);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int launch_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* out) {
+  const double lo[3] = {0.0, 0.0, 0.0};
+  return launch_mesh_coords_box(c, dim, n, lo, L, out);
 }
 
 __device__ __forceinline__ void sort_small(long long* v, int n) {

@@ -24,6 +24,16 @@ def coordinates(dim, n, L, ctx=None):
     return out
 
 
+def coordinates_box(dim, n, lo, hi, ctx=None):
+    """(nverts, dim) float64 on [lo, hi]: IntervalMesh(n, a, b) / RectangleMesh(Point(a..), Point(b..)) / BoxMesh."""
+    ctx = ctx or _lib.default_context()
+    nv, _ = _lib.mesh_counts(dim, n)
+    out = np.empty((nv, dim), dtype=np.float64)
+    _lib.check(_lib.lib().pde_mesh_coords_box(ctx.handle, int(dim), _lib.i3(n), _lib.d3(lo, 0.0), _lib.d3(hi, 0.0),
+                                              _lib.ptr(out)))
+    return out
+
+
 def cells(dim, n, ordered=True, ctx=None):
     """(ncells, dim+1) int32 connectivity; ordered=True is the state after mesh.order()."""
     ctx = ctx or _lib.default_context()

@@ -259,3 +259,140 @@ def _solve_elasticity_3d_static(Lx: float, Ly: float, Lz: float, nx: int, ny: in
     meta = {"name": name, "unit": unit, "pde": "elasticity_3d", "Lx": Lx, "Ly": Ly, "Lz": Lz, "E": E, "nu": nu,
             "body_fx": body_fx, "body_fy": body_fy, "body_fz": body_fz, "quantity": quantity}
     return _finish(coords, val[None, :], [0.0], 3, meta, as_arrays)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# Curvilinear heat tools (reference :769-1464): the same loop on the coordinate-space mesh with one scalar weight
+# ----------------------------------------------------------------------------------------------------------
+_CURVI = {
+    # kind: (dim, weight r-power, sin(x1) factor, weight Expression degree)
+    "1d_cylindrical": (1, 1, 0, 1), "1d_spherical": (1, 2, 0, 2), "2d_cylindrical": (2, 1, 0, 1),
+    "2d_spherical": (2, 2, 1, 2), "3d_spherical": (3, 2, 1, 2),
+}
+
+
+def _curvilinear(kind, lo, hi, n, bc, diffusivity, T_initial, dt, num_steps, steady, source_type, source_value, rtol,
+                 snapshot_stride=1, ctx=None):
+    ctx = ctx or _lib.default_context()
+    dim, rpow, wsin, wdeg = _CURVI[kind]
+    p = _lib.WheatParams()
+    p.dim = dim
+    p.n = _lib.i3(n)
+    p.lo = _lib.d3(lo, 0.0)
+    p.hi = _lib.d3(hi, 1.0)
+    p.weight_rpow, p.weight_sin_axis1, p.weight_degree = rpow, wsin, wdeg
+    p.steady = 1 if steady else 0
+    p.diffusivity = float(diffusivity)
+    p.dt = float(dt)
+    p.num_steps = int(num_steps)
+    p.snapshot_stride = int(snapshot_stride)
+    p.source_value = float(source_value) if source_type == "constant" else 0.0
+    p.T_initial = float(T_initial)
+    p.bc = bc
+    nv, _ = _lib.mesh_counts(dim, n)
+    nsnap = 1 if steady else 1 + int(num_steps) // max(1, int(snapshot_stride))
+    values = np.empty((nsnap, nv), dtype=np.float64)
+    times = np.empty(nsnap, dtype=np.float64)
+    st = _lib.Stats()
+    o = _lib.make_opts(rtol=rtol, precond="jacobi")
+    _lib.check(_lib.lib().pde_wheat_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(values), _lib.ptr(times),
+                                          C.byref(st)))
+    _last_stats.clear()
+    _last_stats.update(st.as_dict())
+    X = mesh.coordinates_box(dim, n, lo, hi, ctx)
+    return X, values, times
+
+
+def _curvi_meta(system, geometry, r_inner, r_outer, source_type, source_value, steady, **extra):
+    meta = {"name": "temperature", "unit": "°C", "pde": "heat", "coordinate_system": system,
+            "geometry_type": geometry, "r_inner": r_inner, "r_outer": r_outer}
+    meta.update(extra)
+    meta.update({"source_type": source_type, "source_value": source_value, "steady": steady})
+    return meta
+
+
+def _radial_bc(r_inner, T_inner, T_outer):
+    faces = {1: T_outer}
+    if r_inner > 1e-10:          # the inner condition is only imposed on an annulus / shell (:811-815, 967-972)
+        faces[0] = T_inner
+    return _lib.make_bc(faces)
+
+
+def _solve_heat_1d_cylindrical_raw(r_inner: float, r_outer: float, nr: int, diffusivity: float, T_inner: float,
+                                   T_outer: float, T_initial: float, dt: float, num_steps: int, steady: bool = False,
+                                   source_type: str = "none", source_value: float = 0.0,
+                                   initial_type: str = "constant", initial_amplitude: float = 1.0, *,
+                                   rtol: float = 1e-10, as_arrays: Optional[bool] = None) -> TimeSeriesField:
+    """1D radial heat equation in cylindrical coordinates, weight r (:769-920)."""
+    X, values, times = _curvilinear("1d_cylindrical", [r_inner], [r_outer], [nr], _radial_bc(r_inner, T_inner, T_outer),
+                                    diffusivity, T_initial, dt, num_steps, steady, source_type, source_value, rtol)
+    order = np.argsort(X[:, 0], kind="stable")
+    meta = _curvi_meta("cylindrical", "cylinder" if r_inner < 1e-10 else "annulus", r_inner, r_outer, source_type,
+                       source_value, steady)
+    return _finish(_embed3(X[order], 1), values[:, order], times, 1, meta, as_arrays)
+
+
+def _solve_heat_1d_spherical_raw(r_inner: float, r_outer: float, nr: int, diffusivity: float, T_inner: float,
+                                 T_outer: float, T_initial: float, dt: float, num_steps: int, steady: bool = False,
+                                 source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
+                                 initial_amplitude: float = 1.0, *, rtol: float = 1e-10,
+                                 as_arrays: Optional[bool] = None) -> TimeSeriesField:
+    """1D radial heat equation in spherical coordinates, weight r^2 (:926-1057)."""
+    X, values, times = _curvilinear("1d_spherical", [r_inner], [r_outer], [nr], _radial_bc(r_inner, T_inner, T_outer),
+                                    diffusivity, T_initial, dt, num_steps, steady, source_type, source_value, rtol)
+    order = np.argsort(X[:, 0], kind="stable")
+    meta = _curvi_meta("spherical", "sphere" if r_inner < 1e-10 else "spherical_shell", r_inner, r_outer, source_type,
+                       source_value, steady)
+    return _finish(_embed3(X[order], 1), values[:, order], times, 1, meta, as_arrays)
+
+
+def _solve_heat_2d_cylindrical_raw(r_inner: float, r_outer: float, z_length: float, nr: int, nz: int,
+                                   diffusivity: float, T_boundary: float, T_initial: float, dt: float, num_steps: int,
+                                   steady: bool = False, source_type: str = "none", source_value: float = 0.0,
+                                   initial_type: str = "constant", initial_amplitude: float = 1.0, *,
+                                   rtol: float = 1e-10, as_arrays: Optional[bool] = None) -> TimeSeriesField:
+    """2D axisymmetric heat equation in the (r, z) plane, weight r (:1063-1185)."""
+    bc = _lib.make_bc({f: T_boundary for f in range(4)})
+    X, values, times = _curvilinear("2d_cylindrical", [r_inner, 0.0], [r_outer, z_length], [nr, nz], bc, diffusivity,
+                                    T_initial, dt, num_steps, steady, source_type, source_value, rtol)
+    coords = np.zeros((X.shape[0], 3))
+    coords[:, 0], coords[:, 2] = X[:, 0], X[:, 1]                 # (r, 0, z)
+    meta = _curvi_meta("cylindrical", "cylinder" if r_inner < 1e-10 else "annular_cylinder", r_inner, r_outer,
+                       source_type, source_value, steady, z_length=z_length)
+    return _finish(coords, values, times, 2, meta, as_arrays)
+
+
+def _solve_heat_2d_spherical_raw(r_inner: float, r_outer: float, nr: int, ntheta: int, diffusivity: float,
+                                 T_boundary: float, T_initial: float, dt: float, num_steps: int, steady: bool = False,
+                                 source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
+                                 initial_amplitude: float = 1.0, *, rtol: float = 1e-10,
+                                 as_arrays: Optional[bool] = None) -> TimeSeriesField:
+    """2D axisymmetric heat equation in the (r, theta) plane, weight r^2 sin(theta) (:1191-1320)."""
+    bc = _lib.make_bc({f: T_boundary for f in range(4)})
+    X, values, times = _curvilinear("2d_spherical", [r_inner, 0.0], [r_outer, float(np.pi)], [nr, ntheta], bc,
+                                    diffusivity, T_initial, dt, num_steps, steady, source_type, source_value, rtol)
+    coords = np.zeros((X.shape[0], 3))
+    coords[:, 0] = X[:, 0] * np.sin(X[:, 1])                      # phi = 0: (r sin(theta), 0, r cos(theta))
+    coords[:, 2] = X[:, 0] * np.cos(X[:, 1])
+    meta = _curvi_meta("spherical", "sphere" if r_inner < 1e-10 else "spherical_shell", r_inner, r_outer, source_type,
+                       source_value, steady)
+    return _finish(coords, values, times, 2, meta, as_arrays)
+
+
+def _solve_heat_3d_spherical_raw(r_inner: float, r_outer: float, nr: int, ntheta: int, nphi: int, diffusivity: float,
+                                 T_boundary: float, T_initial: float, dt: float, num_steps: int, steady: bool = False,
+                                 source_type: str = "none", source_value: float = 0.0, initial_type: str = "constant",
+                                 initial_amplitude: float = 1.0, *, rtol: float = 1e-10,
+                                 as_arrays: Optional[bool] = None) -> TimeSeriesField:
+    """3D heat equation in (r, theta, phi), weight r^2 sin(theta) (:1326-1464)."""
+    bc = _lib.make_bc({f: T_boundary for f in range(6)})
+    X, values, times = _curvilinear("3d_spherical", [r_inner, 0.0, 0.0], [r_outer, float(np.pi), float(2.0 * np.pi)],
+                                    [nr, ntheta, nphi], bc, diffusivity, T_initial, dt, num_steps, steady, source_type,
+                                    source_value, rtol)
+    coords = np.empty((X.shape[0], 3))
+    coords[:, 0] = X[:, 0] * np.sin(X[:, 1]) * np.cos(X[:, 2])
+    coords[:, 1] = X[:, 0] * np.sin(X[:, 1]) * np.sin(X[:, 2])
+    coords[:, 2] = X[:, 0] * np.cos(X[:, 1])
+    meta = _curvi_meta("spherical", "sphere" if r_inner < 1e-10 else "spherical_shell", r_inner, r_outer, source_type,
+                       source_value, steady)
+    return _finish(coords, values, times, 3, meta, as_arrays)

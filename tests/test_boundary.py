@@ -47,7 +47,9 @@ def test_tool_signature_matches_reference(server, name):
 
 @pytest.mark.parametrize("name", ["_solve_heat_1d_raw", "_solve_heat_2d_raw", "_solve_heat_3d_raw",
                                   "_solve_elasticity_1d_static", "_solve_elasticity_2d_static",
-                                  "_solve_elasticity_3d_static"])
+                                  "_solve_elasticity_3d_static", "_solve_heat_1d_cylindrical_raw",
+                                  "_solve_heat_1d_spherical_raw", "_solve_heat_2d_cylindrical_raw",
+                                  "_solve_heat_2d_spherical_raw", "_solve_heat_3d_spherical_raw"])
 def test_raw_solver_signature_is_a_superset(name):
     import pde_solver_b200 as P
     ours = inspect.signature(getattr(P, name))
@@ -80,11 +82,12 @@ def test_cabi_exports_every_declared_symbol():
     assert not missing, missing
 
 
-def test_out_of_scope_tools_raise_clearly(server):
-    with pytest.raises(NotImplementedError, match="outside"):
-        server.solve_heat_1D_cylindrical()
-    with pytest.raises(NotImplementedError):
-        server.solve_heat_3D_spherical()
+def test_unstructured_branches_raise_clearly():
+    import pde_solver_b200 as P
+    with pytest.raises(NotImplementedError, match="cylinder"):
+        P._solve_heat_3d_raw(1, 1, 1, 4, 4, 4, 1.0, 0.0, 20.0, 0.01, 1, geometry_type="cylinder", cylinder_radius=0.5)
+    with pytest.raises(NotImplementedError, match="composite"):
+        P._solve_heat_3d_raw(1, 1, 1, 4, 4, 4, 1.0, 0.0, 20.0, 0.01, 1, core_radius=0.2, core_diffusivity=5.0)
 
 
 def test_plot_tool_accepts_solver_pickles(server, tmp_path):

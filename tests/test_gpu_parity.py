@@ -178,6 +178,35 @@ def test_heat_trig_initial_conditions(P, initial_type):
                 dict(args=(1, 0.5, 0.75, 12, 6, 8, 1.0, 0.0, 0.0, 0.01, 3), kw=ic), "gmg")
 
 
+# ---------------------------------------------------------------- curvilinear heat tools vs oracle LU
+@pytest.mark.parametrize("kind,n,kw", [
+    ("1d_cylindrical", [50], dict(r_inner=0.1, r_outer=1.0, T_inner=100.0, T_outer=20.0)),
+    ("1d_cylindrical", [40], dict(r_inner=0.0, r_outer=1.0, T_inner=100.0, T_outer=20.0)),       # axis r = 0: no inner BC
+    ("1d_spherical", [50], dict(r_inner=0.1, r_outer=1.0, T_inner=100.0, T_outer=20.0)),
+    ("2d_cylindrical", [14, 18], dict(r_inner=0.1, r_outer=1.0, z_length=2.0, T_boundary=35.0)),
+    ("2d_spherical", [12, 16], dict(r_inner=0.1, r_outer=1.0, T_boundary=35.0)),
+    ("3d_spherical", [8, 7, 9], dict(r_inner=0.2, r_outer=1.0, T_boundary=35.0)),
+])
+@pytest.mark.parametrize("steady", [False, True])
+def test_curvilinear_heat_tools(P, kind, n, kw, steady):
+    common = dict(diffusivity=0.8, T_initial=20.0, dt=0.02, num_steps=4, steady=steady, source_type="constant",
+                  source_value=40.0)
+    ref = fo.solve_heat_curvilinear(kind, kw["r_inner"], kw["r_outer"], n, **{k: v for k, v in kw.items()
+                                                                               if k not in ("r_inner", "r_outer")},
+                                    **common)
+    fn = getattr(P, f"_solve_heat_{kind}_raw")
+    names = {"1d_cylindrical": ["nr"], "1d_spherical": ["nr"], "2d_cylindrical": ["nr", "nz"],
+             "2d_spherical": ["nr", "ntheta"], "3d_spherical": ["nr", "ntheta", "nphi"]}[kind]
+    f = fn(**kw, **dict(zip(names, n)), **common, as_arrays=True)
+    assert f.values.shape == ref.values.shape and f.dim == ref.dim
+    assert np.allclose(np.asarray(f.coords), ref.coords, rtol=0, atol=1e-14)
+    assert np.allclose(f.times, ref.times, rtol=0, atol=1e-15)
+    for k in range(ref.values.shape[0]):
+        assert fo.rel_l2(f.values[k], ref.values[k]) <= TOL, (k, fo.rel_l2(f.values[k], ref.values[k]))
+    assert P.last_stats()["converged"] == 1
+    assert f.meta["coordinate_system"] in ("cylindrical", "spherical") and "r_inner" in f.meta
+
+
 # ---------------------------------------------------------------- elasticity vs oracle LU
 @pytest.mark.parametrize("precond", ["jacobi", "gmg"])
 @pytest.mark.parametrize("quantity", ["stress", "strain"])

@@ -147,3 +147,28 @@ def test_project_p2_reproduces_quadratic_moments():
     u = fo.project_p2_expression(m, fn)
     _, M = fo.assemble_stiffness_mass(m)
     assert np.isclose((M @ u).sum(), 1 + 1 / 3 - 1 / 4)
+
+
+def test_weighted_forms_known_answers():
+    # curvilinear tools: weighted mass sums to the integral of the weight (exact for polynomial weights) and the
+    # steady radial solutions converge to the analytic log / 1/r profiles
+    m = fo.interval_mesh(10, 0.5, 2.0)
+    _, M, l = fo.assemble_weighted(m, lambda x: x[:, 0], 1)
+    assert np.isclose(M.sum(), (2.0 ** 2 - 0.5 ** 2) / 2) and np.isclose(l.sum(), M.sum())
+    _, M, l = fo.assemble_weighted(m, lambda x: x[:, 0] ** 2, 2)
+    assert np.isclose(M.sum(), (2.0 ** 3 - 0.5 ** 3) / 3) and np.isclose(l.sum(), M.sum())
+    b = fo.box_mesh((0.5, 0, 0), (2.0, 1.0, 1.0), 3, 2, 2)
+    K, M, l = fo.assemble_weighted(b, lambda x: x[:, 0] ** 2, 2)
+    assert np.isclose(M.sum(), (8 - 0.125) / 3) and np.allclose(K @ np.ones(b.nv), 0, atol=1e-12)
+    K1, M1 = fo.assemble_stiffness_mass(b)
+    Kc, Mc, _ = fo.assemble_weighted(b, lambda x: np.full(x.shape[0], 3.0), 1)      # constant weight = plain forms
+    assert abs(Kc - 3 * K1).max() < 1e-12 and abs(Mc - 3 * M1).max() < 1e-14
+    errs = []
+    for n in (100, 200):
+        f = fo.solve_heat_curvilinear("1d_cylindrical", 0.5, 2.0, [n], 1.0, steady=True, T_inner=100.0, T_outer=20.0)
+        r = f.coords[:, 0]
+        errs.append(np.abs(f.values[0] - (100 - 80 * np.log(r / 0.5) / np.log(4.0))).max())
+    assert errs[1] < errs[0] / 3.5 and errs[1] < 1e-3                                   # O(h^2)
+    f = fo.solve_heat_curvilinear("1d_spherical", 0.5, 2.0, [400], 1.0, steady=True, T_inner=100.0, T_outer=20.0)
+    r = f.coords[:, 0]
+    assert np.abs(f.values[0] - (20 + 80 * (1 / r - 0.5) / 1.5)).max() < 1e-3
