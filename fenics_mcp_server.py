@@ -15,8 +15,8 @@ the JSON-RPC channel, so nothing here or in the CUDA library prints to it.
 
 All eleven solve tools run on the GPU: the six Cartesian ones (box geometry, uniform diffusivity) and the five
 curvilinear heat tools (:2044-2119, 2220-2520; same loop with one scalar weight).  The cylinder
-(mshr) and composite-core branches of solve_heat_3D (:512-572) raise a clear error: unstructured mesh / DG0
-coefficient, outside this build (n4).
+and composite-core branches of solve_heat_3D (:512-572) run as in the reference's deployment, which has no mshr:
+BoxMesh((0,-R,-R),(Lx,R,R)) with the radial weight sqrt(y^2+z^2), DG0 core diffusivity (n4).
 
 Solver knobs the reference does not have come from the environment so existing callers are
 unaffected: PDE_B200_RTOL (default 1e-10), PDE_B200_PRECOND (auto|gmg|jacobi),

@@ -148,6 +148,11 @@ int pde_heat_open(pde_ctx* ctx, const pde_heat_params* p, const pde_solver_opts*
 int pde_heat_set_state(pde_heat_state* s, const double* u_host /* [local nverts] */);
 int pde_heat_step(pde_heat_state* s, int nsteps, pde_stats* st);
 int pde_heat_get_state(pde_heat_state* s, double* u_host /* [local nverts] */);
+/* nreq independent one-step advances u_in[k] -> u_out[k] (each [local nverts], host memory; pinned buffers from
+ * pde_host_alloc give full overlap): upload of request k+1 and download of result k-1 run on separate copy streams
+ * while request k is solved.  Same arithmetic per request as set_state + step(1) + get_state. */
+int pde_heat_advance_batch(pde_heat_state* s, int nreq, const double* const* u_in_host,
+                           double* const* u_out_host, pde_stats* st);
 int64_t pde_heat_local_nverts(pde_heat_state* s);
 int pde_heat_close(pde_heat_state* s);
 
@@ -155,7 +160,8 @@ int pde_heat_close(pde_heat_state* s);
  * Same backward-Euler / steady P1 solve on the coordinate-space mesh [lo,hi] with ONE scalar weight in every term:
  *   a = w u v dx + dt k w grad(u).grad(v) dx,  L = w u_n v dx + dt w f v dx,
  *   w = x0^weight_rpow * (weight_sin_axis1 ? sin(x1) : 1), an Expression of degree weight_degree (1 or 2).
- * The initial state is the constant T_initial (every initial_type of these tools falls back to it). */
+ * The initial state of the curvilinear tools is the constant T_initial (every initial_type falls back to it);
+ * the 3D cylinder / composite-core branches honour initial_type like the box solver. */
 typedef struct pde_wheat_params {
   int32_t dim;
   int32_t n[3];
@@ -171,6 +177,15 @@ typedef struct pde_wheat_params {
   double source_value;
   double T_initial;
   pde_bc bc;
+  /* cylinder / composite-core branches of _solve_heat_3d_raw (:512-572, 642-645; dim 3 only) */
+  int32_t weight_kind;        /* 0: separable weight above; 1: w = sqrt(x1^2 + x2^2) (degree 2), the BoxMesh "cylinder" */
+  int32_t has_core;           /* 1: DG0 diffusivity = core_diffusivity on cells with sqrt(x1^2+x2^2) < core_radius */
+  double core_radius;
+  double core_diffusivity;
+  int32_t initial_type;       /* PDE_IC_CONSTANT / PDE_IC_ZERO / PDE_IC_COSINE / PDE_IC_SINE */
+  int32_t reserved0;
+  double initial_amplitude;
+  double initial_wavenumber;
 } pde_wheat_params;
 int pde_wheat_solve(pde_ctx* ctx, const pde_wheat_params* p, const pde_solver_opts* o,
                     double* values_out /* [nsnap][nverts] */, double* times_out, pde_stats* st);

@@ -582,8 +582,9 @@ def _weight_basis_integrals(d, degree):
     return Ws, Wl, Wm
 
 
-def assemble_weighted(mesh: Mesh, wfun: Callable[[np.ndarray], np.ndarray], degree: int):
-    """(Kw, Mw, mw): int I_p(w) grad(phi_i).grad(phi_j), int I_p(w) phi_i phi_j, int I_p(w) phi_i."""
+def assemble_weighted(mesh: Mesh, wfun: Callable[[np.ndarray], np.ndarray], degree: int, cell_scale=None):
+    """(Kw, Mw, mw): int I_p(w) grad(phi_i).grad(phi_j), int I_p(w) phi_i phi_j, int I_p(w) phi_i.
+    cell_scale: optional per-cell factor of the stiffness term only (a DG0 diffusivity)."""
     d = mesh.dim
     vol, G = _gradients(mesh)
     c = mesh.cells.astype(np.int64)
@@ -595,6 +596,8 @@ def assemble_weighted(mesh: Mesh, wfun: Callable[[np.ndarray], np.ndarray], degr
         wk += [wfun(0.5 * (X[:, a, :] + X[:, b, :])) for a, b in itertools.combinations(range(nv), 2)]
     wk = np.stack(wk, axis=1)                                  # (ncells, nk)
     wbar = wk @ Ws                                             # int I(w) / vol
+    if cell_scale is not None:
+        wbar = wbar * cell_scale
     rows, cols, kv, mv = [], [], [], []
     load = np.zeros(mesh.nv)
     for i in range(nv):
@@ -690,3 +693,80 @@ def solve_heat_curvilinear(kind: str, r_inner: float, r_outer: float, n: Sequenc
         order = np.argsort(mesh.coords[:, 0], kind="stable")
         coords, vals = coords[order], vals[:, order]
     return Field(coords=coords, values=vals, times=np.array(times), dim=dim, meta={"kind": kind})
+
+
+def solve_heat_3d_special(Lx, Ly, Lz, n, diffusivity, T_boundary=0.0, T_initial=20.0, dt=0.01, num_steps=20,
+                          steady=False, source_type="none", source_value=0.0, geometry_type="box",
+                          cylinder_radius=None, T_left=None, T_right=None, T_side=None, core_radius=None,
+                          core_diffusivity=None, initial_type="constant", initial_amplitude=1.0,
+                          initial_wavenumber=1.0) -> Field:
+    """The cylinder / composite-core branches of _solve_heat_3d_raw (:512-572, 576-605, 642-716) as they run in the
+    reference's deployment, i.e. WITHOUT mshr (neither Dockerfile nor requirements.txt install it): the
+    "cylinder" is BoxMesh(Point(0,-R,-R), Point(Lx,R,R), nx, int(ny*2R), int(nz*2R)) with every term weighted by
+    Expression("sqrt(x[1]^2+x[2]^2)", degree=2); a composite core is a DG0 diffusivity equal to core_diffusivity on
+    the cells SubDomain.mark selects for r < core_radius (all vertices and the midpoint inside)."""
+    nx, ny, nz = n
+    cyl = geometry_type == "cylinder" and cylinder_radius is not None
+    if cyl:
+        R = cylinder_radius
+        mesh = box_mesh((0.0, -R, -R), (Lx, R, R), nx, int(ny * R * 2), int(nz * R * 2))
+        wfun, degree = (lambda x: np.sqrt(x[:, 1] ** 2 + x[:, 2] ** 2)), 2
+    else:
+        mesh = box_mesh((0.0, 0.0, 0.0), (Lx, Ly, Lz), nx, ny, nz)
+        wfun, degree = (lambda x: np.ones(x.shape[0])), 1
+    kcell = None
+    if core_radius is not None and core_diffusivity is not None:
+        X = mesh.coords[mesh.cells]                                       # (nc, 4, 3)
+        rv = np.sqrt(X[:, :, 1] ** 2 + X[:, :, 2] ** 2)
+        mid = X.mean(axis=1)
+        inside = (rv < core_radius).all(axis=1) & (np.sqrt(mid[:, 1] ** 2 + mid[:, 2] ** 2) < core_radius)
+        kcell = np.where(inside, float(core_diffusivity), float(diffusivity))
+    else:
+        kcell = np.full(mesh.cells.shape[0], float(diffusivity))
+    Kk, Mw, mw = assemble_weighted(mesh, wfun, degree, cell_scale=kcell)   # Kk already carries kappa
+    directional = T_left is not None or T_right is not None or T_side is not None
+    if directional:
+        bcs = []
+        if cyl:
+            def side(x, ob):
+                r = np.sqrt(x[:, 1] ** 2 + x[:, 2] ** 2)
+                return ob & ~(near(x[:, 0], 0.0) | near(x[:, 0], Lx)) & near(r, cylinder_radius)
+        else:
+            def side(x, ob):
+                return ob & ~(near(x[:, 0], 0.0) | near(x[:, 0], Lx))
+        if T_left is not None:
+            bcs.append((dirichlet_dofs(mesh, lambda x, ob: ob & near(x[:, 0], 0.0)), T_left))
+        if T_right is not None:
+            bcs.append((dirichlet_dofs(mesh, lambda x, ob: ob & near(x[:, 0], Lx)), T_right))
+        if T_side is not None:
+            bcs.append((dirichlet_dofs(mesh, side), T_side))
+    else:
+        bcs = [(dirichlet_dofs(mesh, lambda x, ob: ob), T_boundary)]
+    bc_dofs, bc_vals = _merge_bcs(bcs, mesh.nv)
+    f = float(source_value) if source_type == "constant" else 0.0
+    snaps, times = [], []
+    if steady:
+        A, b = apply_bc_rowwise(Kk.tocsr(), f * mw, bc_dofs, bc_vals)
+        snaps.append(lu_solve(A, b))
+        times.append(0.0)
+    else:
+        if initial_type == "zero":
+            u = np.zeros(mesh.nv)
+        elif initial_type in ("cosine", "sine"):                    # unweighted project(), :674-685
+            u = project_p2_expression(mesh, _initial_expression(3, initial_type, initial_amplitude,
+                                                                initial_wavenumber))
+        else:
+            u = np.full(mesh.nv, float(T_initial))
+        u[bc_dofs] = bc_vals
+        snaps.append(u.copy())
+        times.append(0.0)
+        A, _ = apply_bc_rowwise((Mw + dt * Kk).tocsr(), np.zeros(mesh.nv), bc_dofs, bc_vals)
+        lu = _ScaledLU(A.tocsr())
+        for step in range(num_steps):
+            b = Mw @ u + (dt * f) * mw
+            b[bc_dofs] = bc_vals
+            u = lu.solve(b)
+            snaps.append(u.copy())
+            times.append((step + 1) * dt)
+    return Field(coords=mesh.coords.copy(), values=np.array(snaps), times=np.array(times), dim=3,
+                 meta={"geometry_type": geometry_type})

@@ -51,7 +51,10 @@ class WheatParams(C.Structure):
     _fields_ = [("dim", C.c_int32), ("n", C.c_int32 * 3), ("lo", C.c_double * 3), ("hi", C.c_double * 3),
                 ("weight_rpow", C.c_int32), ("weight_sin_axis1", C.c_int32), ("weight_degree", C.c_int32),
                 ("steady", C.c_int32), ("diffusivity", C.c_double), ("dt", C.c_double), ("num_steps", C.c_int32),
-                ("snapshot_stride", C.c_int32), ("source_value", C.c_double), ("T_initial", C.c_double), ("bc", Bc)]
+                ("snapshot_stride", C.c_int32), ("source_value", C.c_double), ("T_initial", C.c_double), ("bc", Bc),
+                ("weight_kind", C.c_int32), ("has_core", C.c_int32), ("core_radius", C.c_double),
+                ("core_diffusivity", C.c_double), ("initial_type", C.c_int32), ("reserved0", C.c_int32),
+                ("initial_amplitude", C.c_double), ("initial_wavenumber", C.c_double)]
 
 
 class OpParams(C.Structure):
@@ -89,6 +92,7 @@ def lib():
                      "pde_nccl_unique_id", "pde_comm_init", "pde_mesh_counts", "pde_mesh_coords",
                      "pde_mesh_cells", "pde_dofmap_cells", "pde_boundary_mask", "pde_heat_solve",
                      "pde_heat_open", "pde_heat_set_state", "pde_heat_step", "pde_heat_get_state",
+                     "pde_heat_advance_batch",
                      "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench",
                      "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition", "pde_op_manufactured", "pde_halo_bench", "pde_wheat_solve",
                      "pde_mesh_coords_box"):
@@ -327,6 +331,18 @@ class HeatStepper:
     def get_state(self, out):
         check(lib().pde_heat_get_state(self.handle, ptr(out)))
         return out
+
+    def advance_batch(self, inputs, outputs):
+        """Independent one-step advances inputs[k] -> outputs[k] (host arrays of nloc float64, ideally pinned):
+        uploads, solves and downloads are pipelined on three streams (pde_heat_advance_batch)."""
+        n = len(inputs)
+        if len(outputs) != n:
+            raise ValueError("inputs and outputs differ in length")
+        pin = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in inputs])
+        pout = (C.c_void_p * max(1, n))(*[a.ctypes.data for a in outputs])
+        st = Stats()
+        check(lib().pde_heat_advance_batch(self.handle, n, pin, pout, C.byref(st)))
+        return st.as_dict()
 
     def close(self):
         if self.handle:

@@ -32,7 +32,7 @@ extern "C" int pde_ctx_create(int device, pde_ctx** out) {
   CUDA_OK(cudaMalloc(&c->scal, sizeof(double) * S_NSLOTS));
   CUDA_OK(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_NSLOTS, c->stream));
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  CUDA_OK(cudaHostAlloc(&c->h_scal, sizeof(double) * S_NSLOTS, cudaHostAllocDefault));
+  CUDA_OK(cudaHostAlloc(&c->h_scal, sizeof(double) * S_NSLOTS, cudaHostAllocMapped));
   *out = c;
   return 0;
 }
@@ -223,12 +223,79 @@ struct pde_heat_state {
   long long nloc = 0;
   long long steps_done = 0;
   double setup_ms = 0;
+  // copy pipeline (pde_heat_advance_batch, snapshots of pde_heat_solve): two staging buffers per direction and one
+  // stream per direction, so that PCIe traffic in both directions overlaps the solve on the compute stream
+  struct Pipe {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t in_ready[2] = {}, in_free[2] = {}, out_ready[2] = {}, out_free[2] = {};
+    double* in[2] = {nullptr, nullptr};
+    double* out[2] = {nullptr, nullptr};
+    long long nout = 0;      // snapshots handed to the d2h stream so far
+    bool ready = false;
+  } pipe;
 };
+
+static void pipe_release(pde_heat_state* s) {
+  pde_heat_state::Pipe& q = s->pipe;
+  if (q.h2d) { cudaStreamSynchronize(q.h2d); cudaStreamDestroy(q.h2d); }
+  if (q.d2h) { cudaStreamSynchronize(q.d2h); cudaStreamDestroy(q.d2h); }
+  for (int i = 0; i < 2; ++i) {
+    if (q.in_ready[i]) cudaEventDestroy(q.in_ready[i]);
+    if (q.in_free[i]) cudaEventDestroy(q.in_free[i]);
+    if (q.out_ready[i]) cudaEventDestroy(q.out_ready[i]);
+    if (q.out_free[i]) cudaEventDestroy(q.out_free[i]);
+    if (q.in[i]) cudaFree(q.in[i]);
+    if (q.out[i]) cudaFree(q.out[i]);
+  }
+  q = pde_heat_state::Pipe();
+}
+
+static int pipe_init(pde_heat_state* s, bool want_in) {
+  pde_heat_state::Pipe& q = s->pipe;
+  if (!q.ready) {
+    CUDA_OK(cudaStreamCreateWithFlags(&q.h2d, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&q.d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OK(cudaEventCreateWithFlags(&q.in_ready[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&q.in_free[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&q.out_ready[i], cudaEventDisableTiming));
+      CUDA_OK(cudaEventCreateWithFlags(&q.out_free[i], cudaEventDisableTiming));
+      CUDA_OK(cudaMalloc((void**)&q.out[i], sizeof(double) * (s->nloc ? s->nloc : 1)));
+    }
+    q.ready = true;
+  }
+  if (want_in && !q.in[0])
+    for (int i = 0; i < 2; ++i) CUDA_OK(cudaMalloc((void**)&q.in[i], sizeof(double) * (s->nloc ? s->nloc : 1)));
+  return 0;
+}
+
+// pack the current state into a staging buffer on the compute stream and hand it to the d2h stream; returns
+// without waiting for the copy (pipe_drain waits)
+static int pipe_push_snapshot(pde_heat_state* s, double* dst_host) {
+  pde_ctx* c = s->c;
+  pde_heat_state::Pipe& q = s->pipe;
+  const int b = (int)(q.nout & 1);
+  if (q.nout >= 2) CUDA_OK(cudaStreamWaitEvent(c->stream, q.out_free[b], 0));
+  PDE_OK(launch_pack(c, s->g, 1, s->u.p, q.out[b], 0));
+  CUDA_OK(cudaEventRecord(q.out_ready[b], c->stream));
+  CUDA_OK(cudaStreamWaitEvent(q.d2h, q.out_ready[b], 0));
+  CUDA_OK(cudaMemcpyAsync(dst_host, q.out[b], sizeof(double) * s->nloc, cudaMemcpyDeviceToHost, q.d2h));
+  CUDA_OK(cudaEventRecord(q.out_free[b], q.d2h));
+  q.nout += 1;
+  return 0;
+}
+
+static int pipe_drain(pde_heat_state* s) {
+  if (s->pipe.h2d) CUDA_OK(cudaStreamSynchronize(s->pipe.h2d));
+  if (s->pipe.d2h) CUDA_OK(cudaStreamSynchronize(s->pipe.d2h));
+  return 0;
+}
 
 extern "C" int pde_heat_close(pde_heat_state* s) {
   if (!s) return 0;
   cudaSetDevice(s->c->device);
   cudaStreamSynchronize(s->c->stream);
+  pipe_release(s);
   s->A.release(); s->K.release(); s->M.release();
   s->mg.release();
   s->w.release();
@@ -287,39 +354,8 @@ extern "C" int pde_heat_open(pde_ctx* c, const pde_heat_params* p, const pde_sol
     double v0 = p->initial_type == PDE_IC_ZERO ? 0.0 : p->T_initial;
     if (p->steady) v0 = 0.0;
     if (!p->steady && (p->initial_type == PDE_IC_COSINE || p->initial_type == PDE_IC_SINE)) {
-      // u_n = project(Expression(..., degree=2), V) (:276-290, 408-421, 672-685): consistent-mass solve of the
-      // P2-interpolated expression, then bc.apply(u_n.vector())
-      BcDev nobc;
-      std::memset(&nobc, 0, sizeof(nobc));
-      Operator Mf;
-      PcgWork pw;
-      int r2 = 0;
-      do {
-        if ((r2 = Mf.setup_scalar(c, s->g, nobc, 1.0, 0.0))) break;
-        SimplexGeom sg;
-        build_simplex_geom(p->dim, s->g.h, &sg);
-        if ((r2 = launch_p2_load(c, s->g, sg, p->initial_amplitude, p->initial_wavenumber,
-                                 p->initial_type == PDE_IC_SINE, p->n, p->L, s->r.p))) break;
-        if ((r2 = launch_zero(c, s->g, 1, s->u.p))) break;
-        if ((r2 = launch_dot(c, s->g, 1, s->r.p, s->r.p, S_TMP0))) break;
-        if (c->world > 1 && (r2 = comm_allreduce_scal(c, S_TMP0, 1))) break;
-        double bn2;
-        if ((r2 = read_scal(c, S_TMP0, 1, &bn2))) break;
-        if ((r2 = pw.alloc(c, s->g, 1))) break;
-        pde_solver_opts po = s->o;
-        po.precond = PDE_PRECOND_JACOBI;
-        po.rtol = 1e-13;
-        pde_stats pst;
-        std::memset(&pst, 0, sizeof(pst));
-        pst.converged = 1;
-        if ((r2 = pcg_solve(c, Mf, nullptr, pw, s->u.p, s->r.p, bn2, po, &pst))) break;
-        if (!pst.converged) { pde_set_error("initial-condition projection did not converge"); r2 = 1; break; }
-        if ((r2 = launch_apply_bc_values(c, s->g, s->bc, s->u.p))) break;
-      } while (0);
-      cudaStreamSynchronize(c->stream);
-      Mf.release();
-      pw.release();
-      if ((rc = r2)) break;
+      if ((rc = project_trig_ic(c, s->g, s->bc, p->dim, p->n, p->L, nullptr, p->initial_amplitude,
+                                p->initial_wavenumber, p->initial_type == PDE_IC_SINE, s->o, s->u.p, s->r.p))) break;
     } else {
       if ((rc = launch_fill_ic(c, s->g, s->bc, s->u.p, v0, 1))) break;
     }
@@ -426,6 +462,57 @@ extern "C" int pde_heat_step(pde_heat_state* s, int nsteps, pde_stats* st_out) {
   return 0;
 }
 
+// A batch of independent one-step advances u_in[k] -> u_out[k] with HOST buffers (pinned for full overlap): the
+// upload of request k+1 and the download of result k-1 run on their own streams while request k is solved.
+extern "C" int pde_heat_advance_batch(pde_heat_state* s, int nreq, const double* const* u_in_host,
+                                      double* const* u_out_host, pde_stats* st_out) {
+  if (!s || !u_in_host || !u_out_host) PDE_FAIL("null argument");
+  if (nreq < 0) PDE_FAIL("nreq must be >= 0");
+  pde_ctx* c = s->c;
+  CUDA_OK(cudaSetDevice(c->device));
+  PDE_OK(pipe_init(s, true));
+  pde_heat_state::Pipe& q = s->pipe;
+  pde_stats st;
+  stats_init(&st, (long long)s->g.nn[0] * s->g.nn[1] * s->g.nzg);
+  const long long l0 = c->launches;
+  const size_t bytes = sizeof(double) * s->nloc;
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  q.nout = 0;
+  if (nreq > 0) {
+    if (!u_in_host[0]) PDE_FAIL("null input buffer");
+    CUDA_OK(cudaMemcpyAsync(q.in[0], u_in_host[0], bytes, cudaMemcpyHostToDevice, q.h2d));
+    CUDA_OK(cudaEventRecord(q.in_ready[0], q.h2d));
+  }
+  for (int k = 0; k < nreq; ++k) {
+    const int b = k & 1, nb = (k + 1) & 1;
+    if (!u_out_host[k]) PDE_FAIL("null output buffer");
+    if (k + 1 < nreq) {
+      if (!u_in_host[k + 1]) PDE_FAIL("null input buffer");
+      if (k >= 1) CUDA_OK(cudaStreamWaitEvent(q.h2d, q.in_free[nb], 0));
+      CUDA_OK(cudaMemcpyAsync(q.in[nb], u_in_host[k + 1], bytes, cudaMemcpyHostToDevice, q.h2d));
+      CUDA_OK(cudaEventRecord(q.in_ready[nb], q.h2d));
+    }
+    CUDA_OK(cudaStreamWaitEvent(c->stream, q.in_ready[b], 0));
+    PDE_OK(launch_unpack(c, s->g, 1, q.in[b], s->u.p, 0));
+    CUDA_OK(cudaEventRecord(q.in_free[b], c->stream));
+    PDE_OK(launch_apply_bc_values(c, s->g, s->bc, s->u.p));
+    s->steps_done = 0;
+    PDE_OK(heat_one_solve(s, &st));
+    s->steps_done = 1;
+    PDE_OK(pipe_push_snapshot(s, u_out_host[k]));
+  }
+  PDE_OK(pipe_drain(s));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  st.solve_ms = ms;
+  st.setup_ms = s->setup_ms;
+  st.launches = c->launches - l0;
+  if (st_out) *st_out = st;
+  return 0;
+}
+
 extern "C" int pde_heat_solve(pde_ctx* c, const pde_heat_params* p, const pde_solver_opts* o, const double* u0,
                               double* values_out, double* times_out, pde_stats* st_out) {
   if (!values_out || !times_out) PDE_FAIL("null output buffers");
@@ -448,7 +535,11 @@ extern "C" int pde_heat_solve(pde_ctx* c, const pde_heat_params* p, const pde_so
       times_out[0] = 0.0;
       break;
     }
-    if ((rc = pde_heat_get_state(s, values_out))) break;
+    // snapshots leave through the copy pipeline: the D2H of snapshot k overlaps step k+1 (fully when values_out
+    // is pinned host memory; a pageable destination makes the copy call itself blocking, which is still correct)
+    if ((rc = pipe_init(s, false))) break;
+    s->pipe.nout = 0;
+    if ((rc = pipe_push_snapshot(s, values_out))) break;
     times_out[snap++] = 0.0;
     const int stride = p->snapshot_stride > 0 ? p->snapshot_stride : 1;
     for (int step = 0; step < p->num_steps; ++step) {
@@ -462,10 +553,11 @@ extern "C" int pde_heat_solve(pde_ctx* c, const pde_heat_params* p, const pde_so
       acc.solve_ms += st.solve_ms;
       acc.launches += st.launches;
       if ((step + 1) % stride == 0) {
-        if ((rc = pde_heat_get_state(s, values_out + snap * s->nloc))) break;
+        if ((rc = pipe_push_snapshot(s, values_out + snap * s->nloc))) break;
         times_out[snap++] = (step + 1) * p->dt;
       }
     }
+    if (!rc) rc = pipe_drain(s);
     acc.setup_ms = s->setup_ms;
   } while (0);
   pde_heat_close(s);

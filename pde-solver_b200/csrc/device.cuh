@@ -22,7 +22,8 @@ struct pde_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
   ReduceBuf red{};
   double* scal = nullptr;     // device [S_NSLOTS]
-  double* h_scal = nullptr;   // pinned host mirror [S_NSLOTS]
+  double* h_scal = nullptr;   // pinned, mapped host mirror [S_NSLOTS]
+  double* h_scal_dev = nullptr;  // device-side address of h_scal
   long long launches = 0;
   // multi-GPU
   int rank = 0, world = 1;
@@ -217,7 +218,7 @@ int launch_cell_rhs(pde_ctx* c, const Grid& g, int ncomp, const SimplexGeom& sg,
                     int mode, double lam, double mu, double Emod);
 // load vector of project(A*trig(k x)*trig(k y)*trig(k z) interpolated into P2, V)
 int launch_p2_load(pde_ctx* c, const Grid& g, const SimplexGeom& sg, double amp, double kw, int use_sin,
-                   const int32_t n_user[3], const double L_user[3], double* rhs);
+                   const int32_t n_user[3], const double L_user[3], double* rhs, const double* lo_user = nullptr);
 int launch_dense_solve(pde_ctx* c, int n, const double* Ainv, const long long* idx, const double* b, double* x);
 // multi-rank coarse solve: idx[j] < 0 marks dofs owned by another rank
 int launch_dense_gather(pde_ctx* c, int n, const long long* idx, const double* b, double* bglob);

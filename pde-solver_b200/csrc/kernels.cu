@@ -944,12 +944,12 @@ int launch_cell_rhs(pde_ctx* c, const Grid& g, int ncomp, const SimplexGeom& sg,
 // table per axis sampled on the half-step lattice: tab[m] = trig(k * 0.5*(x[m/2] + x[(m+1)/2])).
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_trig_table(int dim, int n, double Ls, int use_sin, double kw, int len, double* __restrict__ tab) {
+k_trig_table(int dim, int n, double lo, double Ls, int use_sin, double kw, int len, double* __restrict__ tab) {
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < len; m += gridDim.x * blockDim.x) {
     const double ia = (double)(m / 2), ib = (double)((m + 1) / 2), dn = (double)n;
-    double xa, xb;
-    if (dim == 3) { xa = __ddiv_rn(__dmul_rn(ia, Ls), dn); xb = __ddiv_rn(__dmul_rn(ib, Ls), dn); }
-    else { xa = __dmul_rn(__ddiv_rn(Ls, dn), ia); xb = __dmul_rn(__ddiv_rn(Ls, dn), ib); }
+    double xa, xb;   // lo + ... with lo = 0 is exact, so the box-at-origin values are unchanged
+    if (dim == 3) { xa = __dadd_rn(lo, __ddiv_rn(__dmul_rn(ia, Ls), dn)); xb = __dadd_rn(lo, __ddiv_rn(__dmul_rn(ib, Ls), dn)); }
+    else { xa = __dadd_rn(lo, __dmul_rn(__ddiv_rn(Ls, dn), ia)); xb = __dadd_rn(lo, __dmul_rn(__ddiv_rn(Ls, dn), ib)); }
     const double x = 0.5 * (xa + xb);
     tab[m] = use_sin ? sin(kw * x) : cos(kw * x);
   }
@@ -1006,7 +1006,7 @@ k_p2_load(const __grid_constant__ Grid g, const __grid_constant__ SimplexGeom sg
 }
 
 int launch_p2_load(pde_ctx* c, const Grid& g, const SimplexGeom& sg, double amp, double kw, int use_sin,
-                   const int32_t n_user[3], const double L_user[3], double* rhs) {
+                   const int32_t n_user[3], const double L_user[3], double* rhs, const double* lo_user) {
   // internal axis of user axis q: dim 2 maps user y -> internal z
   const int dim = g.dim;
   double* tabs[3] = {nullptr, nullptr, nullptr};
@@ -1015,7 +1015,8 @@ int launch_p2_load(pde_ctx* c, const Grid& g, const SimplexGeom& sg, double amp,
     const int iax = (dim == 2 && q == 1) ? 2 : q;
     const int len = 2 * n_user[q] + 1;
     if (cudaMalloc(&tabs[iax], sizeof(double) * len) != cudaSuccess) { pde_set_error("cudaMalloc failed (trig table)"); rc = 1; break; }
-    k_trig_table<<<(len + 255) / 256, 256, 0, c->stream>>>(dim, n_user[q], L_user[q], use_sin, kw, len, tabs[iax]);
+    k_trig_table<<<(len + 255) / 256, 256, 0, c->stream>>>(dim, n_user[q], lo_user ? lo_user[q] : 0.0, L_user[q], use_sin, kw, len,
+                                                           tabs[iax]);
     c->launches++;
   }
   if (!rc) {

@@ -93,11 +93,60 @@ void Operator::release() {
   dev.coef = dev.dinv = dev.load = nullptr;
 }
 
+// Scalars reach the host through mapped pinned memory written by a one-warp kernel, not through a copy engine: a
+// cudaMemcpyAsync poll would queue behind the GB-sized snapshot transfers that run on the copy streams
+// (pde_heat_advance_batch) and stall every convergence check for the length of a transfer.
+__global__ void k_publish_scal(const double* __restrict__ src, double* __restrict__ dst_host, int count) {
+  if ((int)threadIdx.x < count) dst_host[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+
 int read_scal(pde_ctx* c, int slot, int count, double* out) {
-  CUDA_OK(cudaMemcpyAsync(c->h_scal + slot, c->scal + slot, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (count > 32) PDE_FAIL("read_scal: at most 32 slots per call");
+  if (!c->h_scal_dev) CUDA_OK(cudaHostGetDevicePointer((void**)&c->h_scal_dev, c->h_scal, 0));
+  k_publish_scal<<<1, 32, 0, c->stream>>>(c->scal + slot, c->h_scal_dev + slot, count);
+  c->launches++;
   CUDA_OK(cudaStreamSynchronize(c->stream));
-  for (int i = 0; i < count; ++i) out[i] = c->h_scal[slot + i];
+  for (int i = 0; i < count; ++i) out[i] = ((volatile double*)c->h_scal)[slot + i];
   return 0;
+}
+
+// u = project(Expression("A cos(k x0) cos(k x1) ...", degree=2), V), then bc.apply(u) (reference :276-290, 408-421,
+// 672-685): consistent-mass Jacobi-PCG (rtol 1e-13) of the exactly integrated P2-interpolated expression.  `rhs` is
+// scratch; lo_user shifts the box (nullptr: box at the origin).
+int project_trig_ic(pde_ctx* c, const Grid& g, const BcDev& bc, int dim, const int32_t n_user[3], const double L_user[3],
+                    const double* lo_user, double amp, double kw, int use_sin, const pde_solver_opts& o, double* u,
+                    double* rhs) {
+  BcDev nobc;
+  std::memset(&nobc, 0, sizeof(nobc));
+  Operator Mf;
+  PcgWork pw;
+  int rc = 0;
+  do {
+    if ((rc = Mf.setup_scalar(c, g, nobc, 1.0, 0.0))) break;
+    SimplexGeom sg;
+    build_simplex_geom(dim, g.h, &sg);
+    if ((rc = launch_p2_load(c, g, sg, amp, kw, use_sin, n_user, L_user, rhs, lo_user))) break;
+    if ((rc = launch_zero(c, g, 1, u))) break;
+    if ((rc = launch_dot(c, g, 1, rhs, rhs, S_TMP0))) break;
+    if (c->world > 1 && (rc = comm_allreduce_scal(c, S_TMP0, 1))) break;
+    double bn2;
+    if ((rc = read_scal(c, S_TMP0, 1, &bn2))) break;
+    if ((rc = pw.alloc(c, g, 1))) break;
+    pde_solver_opts po = o;
+    po.precond = PDE_PRECOND_JACOBI;
+    po.rtol = 1e-13;
+    pde_stats pst;
+    std::memset(&pst, 0, sizeof(pst));
+    pst.converged = 1;
+    if ((rc = pcg_solve(c, Mf, nullptr, pw, u, rhs, bn2, po, &pst))) break;
+    if (!pst.converged) { pde_set_error("initial-condition projection did not converge"); rc = 1; break; }
+    if ((rc = launch_apply_bc_values(c, g, bc, u))) break;
+  } while (0);
+  cudaStreamSynchronize(c->stream);
+  Mf.release();
+  pw.release();
+  return rc;
 }
 
 // ---- multigrid ---------------------------------------------------------------------------------

@@ -59,5 +59,8 @@ struct PcgWork {
 int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* x, double* r, double bnorm2,
               const pde_solver_opts& o, pde_stats* st);
 
+int project_trig_ic(pde_ctx* c, const Grid& g, const BcDev& bc, int dim, const int32_t n_user[3], const double L_user[3],
+                    const double* lo_user, double amp, double kw, int use_sin, const pde_solver_opts& o, double* u,
+                    double* rhs);
 int read_scal(pde_ctx* c, int slot, int count, double* out);
 int choose_precond(const pde_solver_opts& o, pde_ctx* c, long long ndofs, const Hierarchy& h);

@@ -7,6 +7,12 @@
 // per axis on the half-step lattice.  The operator is no longer a constant stencil: k_wassemble writes the 15
 // (7 / 3) stencil coefficients of every node once, k_vapply applies them, and a Jacobi-PCG with device-side
 // scalars solves the systems (these tools run modest grids; multigrid is not needed).
+//
+// The cylinder / composite-core branches of _solve_heat_3d_raw (:512-572, 642-645) run through the same kernels: the
+// reference's deployment has no mshr (neither Dockerfile nor requirements.txt install it), so its "cylinder" is
+// BoxMesh((0,-R,-R),(Lx,R,R)) with every term weighted by Expression("sqrt(x[1]^2+x[2]^2)", degree=2)
+// (weight_kind 1: not separable, evaluated from the y/z coordinate tables), and a composite core is a DG0
+// diffusivity: core_diffusivity on the cells whose vertices and midpoint all have sqrt(y^2+z^2) < core_radius.
 #include <cmath>
 #include <cstring>
 
@@ -95,8 +101,9 @@ k_weight_table(int dim, int n, double lo, double hi, int rpow, int use_sin, int 
 __global__ void __launch_bounds__(128)
 k_wassemble(const __grid_constant__ Grid g, const __grid_constant__ SimplexGeom sg, const __grid_constant__ WeightInts wi,
             double alpha, double beta, const double* __restrict__ tx, const double* __restrict__ ty,
-            const double* __restrict__ tz, double* __restrict__ coefA, double* __restrict__ coefM,
-            double* __restrict__ loadv) {
+            const double* __restrict__ tz, const double* __restrict__ cyt, const double* __restrict__ czt,
+            int radial_yz, double core_radius, double beta_core,
+            double* __restrict__ coefA, double* __restrict__ coefM, double* __restrict__ loadv) {
   const long long rows = (long long)g.nn[1] * g.nzl;
   for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
        row += (long long)gridDim.x * blockDim.y) {
@@ -119,6 +126,11 @@ k_wassemble(const __grid_constant__ Grid g, const __grid_constant__ SimplexGeom 
             if (sg.corner[t][a] == o) li = a;
           if (li < 0) continue;
           auto val = [&](int ca, int cb) {
+            if (radial_yz) {  // w = sqrt(y^2 + z^2) at the vertex / edge midpoint
+              const double yy = cyt[2 * cy + ((ca >> 1) & 1) + ((cb >> 1) & 1)];
+              const double zz = czt[2 * cz + ((ca >> 2) & 1) + ((cb >> 2) & 1)];
+              return sqrt(yy * yy + zz * zz);
+            }
             double v = tx[2 * cx + (ca & 1) + (cb & 1)];
             if (g.nc[1] > 0) v *= ty[2 * cy + ((ca >> 1) & 1) + ((cb >> 1) & 1)];
             if (g.nc[2] > 0) v *= tz[2 * cz + ((ca >> 2) & 1) + ((cb >> 2) & 1)];
@@ -129,6 +141,21 @@ k_wassemble(const __grid_constant__ Grid g, const __grid_constant__ SimplexGeom 
           for (int e = 0; e < wi.nk - wi.nv; ++e) wk[wi.nv + e] = val(sg.corner[t][wi.ea[e]], sg.corner[t][wi.eb[e]]);
           double wbar = 0.0, wl = 0.0;
           for (int k = 0; k < wi.nk; ++k) { wbar = fma(wk[k], wi.Ws[k], wbar); wl = fma(wk[k], wi.Wl[k][li], wl); }
+          double beta_t = beta;
+          if (core_radius >= 0.0) {
+            // SubDomain.mark (check_midpoint = true): every vertex and the cell midpoint inside r < core_radius
+            bool inside = true;
+            double my = 0.0, mz = 0.0;
+            for (int a = 0; a < sg.nv; ++a) {
+              const int ca = sg.corner[t][a];
+              const double yy = cyt[2 * cy + 2 * ((ca >> 1) & 1)], zz = czt[2 * cz + 2 * ((ca >> 2) & 1)];
+              inside = inside && (sqrt(yy * yy + zz * zz) < core_radius);
+              my += yy; mz += zz;
+            }
+            my /= (double)sg.nv; mz /= (double)sg.nv;
+            inside = inside && (sqrt(my * my + mz * mz) < core_radius);
+            if (inside) beta_t = beta_core;
+          }
           ld = fma(sg.vol, wl, ld);
           for (int b = 0; b < sg.nv; ++b) {
             const int cb = sg.corner[t][b];
@@ -142,7 +169,7 @@ k_wassemble(const __grid_constant__ Grid g, const __grid_constant__ SimplexGeom 
             for (int k = 0; k < wi.nk; ++k) wm = fma(wk[k], wi.Wm[k][li][b], wm);
             const double m = sg.vol * wm, kv = sg.vol * wbar * gg;
             cM[kk] += m;
-            cA[kk] += alpha * m + beta * kv;
+            cA[kk] += alpha * m + beta_t * kv;
           }
         }
       }
@@ -303,6 +330,9 @@ extern "C" int pde_wheat_solve(pde_ctx* c, const pde_wheat_params* p, const pde_
   if (p->dim < 1 || p->dim > 3) PDE_FAIL("dim must be 1, 2 or 3");
   if (p->weight_degree != 1 && p->weight_degree != 2) PDE_FAIL("weight_degree must be 1 or 2");
   if (p->weight_rpow < 0 || p->weight_rpow > 2) PDE_FAIL("weight_rpow must be 0, 1 or 2");
+  if (p->weight_kind != 0 && p->weight_kind != 1) PDE_FAIL("weight_kind must be 0 (separable) or 1 (radial y-z)");
+  if ((p->weight_kind == 1 || p->has_core) && p->dim != 3) PDE_FAIL("radial y-z weight / composite core need dim 3");
+  if (p->has_core && !(p->core_diffusivity > 0)) PDE_FAIL("core_diffusivity must be > 0");
   if (!p->steady && !(p->dt > 0)) PDE_FAIL("dt must be > 0");
   if (!(p->diffusivity > 0)) PDE_FAIL("diffusivity must be > 0");
   pde_solver_opts o;
@@ -336,6 +366,16 @@ extern "C" int pde_wheat_solve(pde_ctx* c, const pde_wheat_params* p, const pde_
                                                              len, tabs[iax]);
     c->launches++;
   }
+  // y / z coordinate tables on the half-step lattice (radial weight, core marking)
+  double* ctabs[2] = {nullptr, nullptr};
+  struct CTabRel { double** t; ~CTabRel() { for (int q = 0; q < 2; ++q) if (t[q]) cudaFree(t[q]); } } ctabrel{ctabs};
+  if (p->weight_kind == 1 || p->has_core)
+    for (int q = 1; q < 3; ++q) {
+      const int len = 2 * p->n[q] + 1;
+      CUDA_OK(cudaMalloc(&ctabs[q - 1], sizeof(double) * len));
+      k_weight_table<<<(len + 255) / 256, 256, 0, c->stream>>>(3, p->n[q], p->lo[q], p->hi[q], 1, 0, len, ctabs[q - 1]);
+      c->launches++;
+    }
   SimplexGeom sg;
   build_simplex_geom(p->dim, g.h, &sg);
   WeightInts wi;
@@ -344,7 +384,10 @@ extern "C" int pde_wheat_solve(pde_ctx* c, const pde_wheat_params* p, const pde_
   const double alpha = p->steady ? 0.0 : 1.0, beta = p->steady ? kappa : p->dt * kappa;
   RowLaunch rl = row_launch(c, g);
   k_wassemble<<<rl.grid, rl.block, 0, c->stream>>>(g, sg, wi, alpha, beta, tabs[0], tabs[1] ? tabs[1] : tabs[0],
-                                                   tabs[2] ? tabs[2] : tabs[0], s.coefA.p, s.coefM.p, s.loadv.p);
+                                                   tabs[2] ? tabs[2] : tabs[0], ctabs[0], ctabs[1], p->weight_kind == 1,
+                                                   p->has_core ? p->core_radius : -1.0,
+                                                   p->steady ? p->core_diffusivity : p->dt * p->core_diffusivity,
+                                                   s.coefA.p, s.coefM.p, s.loadv.p);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   pde_stats st;
@@ -364,8 +407,15 @@ extern "C" int pde_wheat_solve(pde_ctx* c, const pde_wheat_params* p, const pde_
   };
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
   const long long l0 = c->launches;
-  // initial state / Dirichlet lift: every initial_type of these tools falls back to the constant (:893-896 ...)
-  PDE_OK(launch_fill_ic(c, g, s.bc, s.u.p, p->steady ? 0.0 : p->T_initial, 1));
+  // initial state / Dirichlet lift: every initial_type of the curvilinear tools falls back to the constant
+  // (:893-896 ...); the 3D cylinder / composite branches keep zero and the (unweighted) cosine / sine projection
+  if (!p->steady && (p->initial_type == PDE_IC_COSINE || p->initial_type == PDE_IC_SINE)) {
+    PDE_OK(project_trig_ic(c, g, s.bc, p->dim, p->n, L, p->lo, p->initial_amplitude, p->initial_wavenumber,
+                           p->initial_type == PDE_IC_SINE, o, s.u.p, s.r.p));
+  } else {
+    const double v0 = (p->steady || p->initial_type == PDE_IC_ZERO) ? 0.0 : p->T_initial;
+    PDE_OK(launch_fill_ic(c, g, s.bc, s.u.p, v0, 1));
+  }
   long long snap = 0;
   if (p->steady) {
     // r0 = f m_w - k K_w u_lift  (A = k K_w)

@@ -166,13 +166,13 @@ def _solve_heat_3d_raw(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: in
                        snapshot_stride: int = 1, as_arrays: Optional[bool] = None, u0=None,
                        stream_to=None) -> TimeSeriesField:
     """3D heat equation on the box [0,Lx]x[0,Ly]x[0,Lz]; uniform or directional Dirichlet values."""
-    if geometry_type == "cylinder" and cylinder_radius is not None:
-        raise NotImplementedError(
-            "geometry_type='cylinder' (mshr / radially weighted forms, reference :512-530, 642-645) is outside "
-            "the structured-box hot path of this build")
-    if core_radius is not None and core_diffusivity is not None:
-        raise NotImplementedError(
-            "composite core (DG0 variable diffusivity, reference :537-572) is outside the uniform-kappa hot path")
+    cyl = geometry_type == "cylinder" and cylinder_radius is not None
+    has_core = core_radius is not None and core_diffusivity is not None
+    if cyl or has_core:
+        return _heat_3d_special(Lx, Ly, Lz, nx, ny, nz, diffusivity, T_boundary, T_initial, dt, num_steps, steady,
+                                source_type, source_value, initial_type, initial_amplitude, initial_wavenumber,
+                                geometry_type, cylinder_radius, T_left, T_right, T_side, core_radius,
+                                core_diffusivity, rtol, snapshot_stride, as_arrays)
     bc = mesh.heat_bc(3, T_boundary=T_boundary, T_left=T_left, T_right=T_right, T_side=T_side)
     coords, values, times = _heat(3, [Lx, Ly, Lz], [nx, ny, nz], diffusivity, T_initial, dt, num_steps, steady,
                                   source_type, source_value, initial_type, initial_amplitude, initial_wavenumber,
@@ -189,6 +189,91 @@ def _solve_heat_3d_raw(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: in
     else:
         meta["T_boundary"] = T_boundary
     meta["diffusivity"] = diffusivity
+    return _finish(coords, values, times, 3, meta, as_arrays)
+
+
+def _heat_3d_special(Lx, Ly, Lz, nx, ny, nz, diffusivity, T_boundary, T_initial, dt, num_steps, steady, source_type,
+                     source_value, initial_type, initial_amplitude, initial_wavenumber, geometry_type,
+                     cylinder_radius, T_left, T_right, T_side, core_radius, core_diffusivity, rtol, snapshot_stride,
+                     as_arrays, ctx=None):
+    """Cylinder / composite-core branches of _solve_heat_3d_raw (:512-572, 576-605, 642-645) as the reference's
+    deployment runs them (no mshr in Dockerfile / requirements.txt, so MSHR_AVAILABLE is False): the "cylinder" is
+    BoxMesh((0,-R,-R),(Lx,R,R), nx, int(ny*2R), int(nz*2R)) with every term weighted by
+    Expression("sqrt(x[1]^2+x[2]^2)", degree=2); the core is a DG0 diffusivity marked by SubDomain.mark."""
+    ctx = ctx or _lib.default_context()
+    cyl = geometry_type == "cylinder" and cylinder_radius is not None
+    has_core = core_radius is not None and core_diffusivity is not None
+    if cyl:
+        R = float(cylinder_radius)
+        lo, hi = [0.0, -R, -R], [float(Lx), R, R]
+        n = [int(nx), int(ny * R * 2), int(nz * R * 2)]
+    else:
+        lo, hi = [0.0, 0.0, 0.0], [float(Lx), float(Ly), float(Lz)]
+        n = [int(nx), int(ny), int(nz)]
+    if min(n) < 1:
+        raise ValueError(f"BoxMesh needs at least one cell per axis, got {n}")
+    directional = T_left is not None or T_right is not None or T_side is not None
+    if not directional:
+        bc = mesh.heat_bc(3, T_boundary=T_boundary)
+    elif geometry_type == "cylinder":
+        # side_boundary_cylinder (:594-598) asks for near(r, R) on boundary facets away from the x ends; on the
+        # BoxMesh no facet has all vertices and its midpoint at r == R, so DOLFIN's topological search finds none
+        # and T_side constrains nothing; left / right are the x-end faces
+        bc = _lib.make_bc({f: v for f, v in ((0, T_left), (1, T_right)) if v is not None})
+    else:
+        bc = mesh.heat_bc(3, T_left=T_left, T_right=T_right, T_side=T_side)
+    p = _lib.WheatParams()
+    p.dim = 3
+    p.n = _lib.i3(n)
+    p.lo = _lib.d3(lo, 0.0)
+    p.hi = _lib.d3(hi, 1.0)
+    p.weight_rpow, p.weight_sin_axis1 = 0, 0
+    p.weight_degree = 2 if cyl else 1
+    p.weight_kind = 1 if cyl else 0
+    p.has_core = 1 if has_core else 0
+    p.core_radius = float(core_radius) if has_core else 0.0
+    p.core_diffusivity = float(core_diffusivity) if has_core else 0.0
+    p.steady = 1 if steady else 0
+    p.diffusivity = float(diffusivity)
+    p.dt = float(dt)
+    p.num_steps = int(num_steps)
+    p.snapshot_stride = int(snapshot_stride)
+    p.source_value = float(source_value) if source_type == "constant" else 0.0
+    p.T_initial = float(T_initial)
+    p.initial_type = _lib.IC.get(initial_type, _lib.IC["constant"])
+    p.initial_amplitude = float(initial_amplitude)
+    p.initial_wavenumber = float(initial_wavenumber)
+    p.bc = bc
+    nv, _ = _lib.mesh_counts(3, n)
+    nsnap = 1 if steady else 1 + int(num_steps) // max(1, int(snapshot_stride))
+    values = np.empty((nsnap, nv), dtype=np.float64)
+    times = np.empty(nsnap, dtype=np.float64)
+    st = _lib.Stats()
+    o = _lib.make_opts(rtol=rtol, precond="jacobi")
+    _lib.check(_lib.lib().pde_wheat_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(values), _lib.ptr(times),
+                                          C.byref(st)))
+    _last_stats.clear()
+    _last_stats.update(st.as_dict())
+    coords = mesh.coordinates_box(3, n, lo, hi, ctx)
+    box = geometry_type == "box"
+    meta = {"name": "temperature", "unit": "°C", "pde": "heat",
+            "coordinate_system": "cartesian" if box else "cylindrical", "Lx": Lx,
+            "Ly": Ly if box else (cylinder_radius * 2 if cylinder_radius else Ly),
+            "Lz": Lz if box else (cylinder_radius * 2 if cylinder_radius else Lz),
+            "geometry_type": geometry_type, "source_type": source_type, "source_value": source_value,
+            "steady": steady}
+    if cyl:
+        meta["cylinder_radius"] = cylinder_radius
+    if directional:
+        for k, v in (("T_left", T_left), ("T_right", T_right), ("T_side", T_side)):
+            if v is not None:
+                meta[k] = v
+    else:
+        meta["T_boundary"] = T_boundary
+    if has_core:
+        meta.update(core_radius=core_radius, core_diffusivity=core_diffusivity, base_diffusivity=diffusivity)
+    else:
+        meta["diffusivity"] = diffusivity
     return _finish(coords, values, times, 3, meta, as_arrays)
 
 

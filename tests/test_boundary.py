@@ -82,11 +82,21 @@ def test_cabi_exports_every_declared_symbol():
     assert not missing, missing
 
 
-def test_unstructured_branches_raise_clearly():
+def test_cylinder_and_composite_branches_reach_the_cuda_library():
+    """geometry_type='cylinder' and core_radius/core_diffusivity are served (reference :512-572 without mshr); on a
+    box without a GPU they must fail in the CUDA layer, never fall back to a CPU path."""
     import pde_solver_b200 as P
-    with pytest.raises(NotImplementedError, match="cylinder"):
+    from pde_solver_b200 import _lib
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("covered by the gpu parity tests")
+    with pytest.raises(_lib.PdeError):
         P._solve_heat_3d_raw(1, 1, 1, 4, 4, 4, 1.0, 0.0, 20.0, 0.01, 1, geometry_type="cylinder", cylinder_radius=0.5)
-    with pytest.raises(NotImplementedError, match="composite"):
+    with pytest.raises(_lib.PdeError):
         P._solve_heat_3d_raw(1, 1, 1, 4, 4, 4, 1.0, 0.0, 20.0, 0.01, 1, core_radius=0.2, core_diffusivity=5.0)
 
 

@@ -299,3 +299,80 @@ def test_multi_gpu_slabs_match_oracle():
                         os.path.join(root, "scripts", "mgpu_check.py")], stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=600, cwd=root)
     assert r.returncode == 0 and "MGPU OK" in r.stdout, r.stdout[-3000:]
+
+
+# ---------------------------------------------------------------- pipelined batch of one-step advances
+def test_heat_advance_batch_matches_oracle_and_serial_calls(P, ctx):
+    """pde_heat_advance_batch (3-stream upload / solve / download pipeline) == set_state + step + get_state, and
+    each result is one backward-Euler step of the oracle from the same input field."""
+    n, L, kappa, dt = [12, 10, 9], [1.0, 0.8, 0.6], 0.7, 0.02
+    m = fo.make_mesh(3, L, n)
+    K, M = fo.assemble_stiffness_mass(m)
+    dofs, vals = fo._merge_bcs(fo.heat_bcs(m, L, T_boundary=2.0), m.nv)
+    A, _ = fo.apply_bc_rowwise((M + dt * kappa * K).tocsr(), np.zeros(m.nv), dofs, vals)
+    rng = np.random.default_rng(5)
+    nreq = 5
+    bc = P._lib.make_bc({f: 2.0 for f in range(6)})
+    for precond in ("jacobi", "gmg"):
+        hs = P._lib.HeatStepper(ctx, 3, n, L, kappa, dt, T_initial=0.0, bc=bc,
+                                opts=P._lib.make_opts(rtol=1e-10, precond=precond))
+        assert hs.nloc == m.nv
+        ins = [P._lib.PinnedArray(m.nv) for _ in range(nreq)]
+        outs = [P._lib.PinnedArray(m.nv) for _ in range(nreq)]
+        for a in ins:
+            a.array[:] = rng.standard_normal(m.nv) * 5.0 + 3.0
+        st = hs.advance_batch([a.array for a in ins], [a.array for a in outs])
+        assert st["converged"] and st["solves"] == nreq
+        tmp = np.empty(m.nv)
+        for a, o in zip(ins, outs):
+            u = a.array.copy()
+            u[dofs] = vals                                   # bc.apply(u_n.vector())
+            b = M @ u
+            b[dofs] = vals
+            ref = fo.lu_solve(A, b)
+            assert np.linalg.norm(o.array - ref) <= TOL * np.linalg.norm(ref)
+            hs.set_state(a.array)
+            hs.step(1)
+            hs.get_state(tmp)
+            assert np.linalg.norm(o.array - tmp) <= 1e-12 * np.linalg.norm(tmp)
+        hs.advance_batch([], [])
+        hs.close()
+        for a in ins + outs:
+            a.free()
+
+
+# ---------------------------------------------------------------- cylinder / composite-core branches of solve_heat_3D
+@pytest.mark.parametrize("case", [
+    dict(geometry_type="cylinder", cylinder_radius=0.3, T_boundary=1.0, T_initial=5.0, source_type="constant",
+         source_value=3.0),
+    dict(geometry_type="cylinder", cylinder_radius=0.3, T_left=10.0, T_right=2.0, T_side=50.0, T_initial=4.0),
+    dict(geometry_type="cylinder", cylinder_radius=0.25, T_side=7.0, T_initial=4.0, source_type="constant",
+         source_value=1.0),
+    dict(core_radius=0.3, core_diffusivity=25.0, T_boundary=0.0, T_initial=3.0),
+    dict(core_radius=0.3, core_diffusivity=25.0, T_left=1.0, T_side=2.0, T_initial=3.0),
+    dict(geometry_type="cylinder", cylinder_radius=0.3, core_radius=0.15, core_diffusivity=8.0, steady=True,
+         T_boundary=2.0, source_type="constant", source_value=5.0),
+    dict(core_radius=0.3, core_diffusivity=4.0, T_boundary=0.5, initial_type="cosine", initial_amplitude=2.0,
+         initial_wavenumber=3.0),
+    dict(geometry_type="cylinder", cylinder_radius=0.3, T_boundary=0.0, initial_type="sine", initial_amplitude=1.5,
+         initial_wavenumber=4.0),
+    dict(geometry_type="cylinder", cylinder_radius=0.3, T_boundary=0.0, initial_type="zero", source_type="constant",
+         source_value=2.0),
+])
+def test_heat_3d_cylinder_and_composite_core(P, case):
+    Lx, Ly, Lz, n, kappa = 1.0, 0.5, 0.5, [6, 10, 10], 0.8
+    kw = dict(dt=0.02, num_steps=3)
+    kw.update(case)
+    ref = fo.solve_heat_3d_special(Lx, Ly, Lz, n, kappa, **kw)
+    args = dict(T_boundary=0.0, T_initial=0.0, steady=False)
+    args.update(kw)
+    f = P._solve_heat_3d_raw(Lx, Ly, Lz, n[0], n[1], n[2], kappa, args.pop("T_boundary"), args.pop("T_initial"),
+                             args.pop("dt"), args.pop("num_steps"), as_arrays=True, **args)
+    assert np.array_equal(np.asarray(f.coords), ref.coords)                 # shifted BoxMesh coordinates bit-exact
+    v = np.asarray(f.values)
+    assert v.shape == ref.values.shape
+    for a, b in zip(v, ref.values):
+        assert np.linalg.norm(a - b) <= TOL * max(np.linalg.norm(b), 1e-300)
+    assert f.meta["geometry_type"] == case.get("geometry_type", "box")
+    if "core_radius" in case:
+        assert f.meta["base_diffusivity"] == kappa and "diffusivity" not in f.meta

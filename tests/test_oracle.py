@@ -172,3 +172,40 @@ def test_weighted_forms_known_answers():
     f = fo.solve_heat_curvilinear("1d_spherical", 0.5, 2.0, [400], 1.0, steady=True, T_inner=100.0, T_outer=20.0)
     r = f.coords[:, 0]
     assert np.abs(f.values[0] - (20 + 80 * (1 / r - 0.5) / 1.5)).max() < 1e-3
+
+
+# ---------------------------------------------------------------- cylinder / composite-core branches of solve_heat_3D
+def test_special_3d_reduces_to_box_solver():
+    """solve_heat_3d_special with unit weight and a core of the same diffusivity is the plain box solve."""
+    kw = dict(T_boundary=1.0, T_initial=4.0, dt=0.02, num_steps=3, source_type="constant", source_value=2.0)
+    ref = fo.solve_heat(3, [1.0, 0.5, 0.4], [5, 4, 3], 0.7, **kw)
+    a = fo.solve_heat_3d_special(1.0, 0.5, 0.4, [5, 4, 3], 0.7, core_radius=0.3, core_diffusivity=0.7, **kw)
+    assert np.allclose(a.values, ref.values, rtol=0, atol=1e-12 * np.abs(ref.values).max())
+    assert np.array_equal(a.coords, ref.coords)
+
+
+def test_special_3d_cylinder_mesh_and_side_set():
+    """The BoxMesh 'cylinder' (:527-529): box [0,Lx]x[-R,R]^2 with int(ny*2R) cells; side_boundary_cylinder finds no
+    facet (no boundary facet of the box has all its vertices at r == R), so T_side alone constrains nothing and the
+    first step from a constant state with no source leaves it constant."""
+    R = 0.3
+    f = fo.solve_heat_3d_special(1.0, 9.0, 9.0, [4, 10, 10], 1.0, T_initial=5.0, dt=0.01, num_steps=2,
+                                 geometry_type="cylinder", cylinder_radius=R, T_side=100.0)
+    assert f.coords.shape[0] == 5 * 7 * 7
+    assert f.coords[:, 1].min() == -R and f.coords[:, 2].max() == R
+    assert np.allclose(f.values, 5.0, rtol=0, atol=1e-10)
+
+
+def test_special_3d_core_marks_cells_by_vertices_and_midpoint():
+    m = fo.box_mesh((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), 2, 4, 4)
+    X = m.coords[m.cells]
+    rv = np.sqrt(X[:, :, 1] ** 2 + X[:, :, 2] ** 2)
+    inside = (rv < 0.6).all(axis=1)
+    # quarter disc of radius 0.6 on the 0.25 lattice: (y,z) lattice points (j,k) with j^2+k^2 < 5.76 are j,k in {0,1,2}
+    # except (2,2).  Footprint cells (0,0),(0,1),(1,0) lie inside with all 6 tets; every Kuhn tet of cell (1,1) contains
+    # the far corner (2,2), so none of its tets is marked: 3 cells x 6 tets x 2 cells along x
+    assert inside.sum() == 36
+    f0 = fo.solve_heat_3d_special(1.0, 1.0, 1.0, [2, 4, 4], 1.0, T_initial=3.0, dt=0.05, num_steps=2,
+                                  core_radius=0.6, core_diffusivity=50.0)
+    f1 = fo.solve_heat_3d_special(1.0, 1.0, 1.0, [2, 4, 4], 1.0, T_initial=3.0, dt=0.05, num_steps=2)
+    assert np.abs(f0.values[-1] - f1.values[-1]).max() > 1e-3      # the core changes the solution
