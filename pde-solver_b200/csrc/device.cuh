@@ -193,7 +193,7 @@ int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, doub
                      const double* q, int slot_rho, int slot_pap, int slot_rho_new, int slot_rr, int jacobi);
 // p = z + beta p with z = dinv r (jacobi) or z given; beta = rho_new/rho (first: beta = 0)
 int launch_cg_pupdate(pde_ctx* c, const Grid& g, const OpDev& op, double* p, const double* r_or_z,
-                      int slot_rho, int slot_rho_new, int first, int jacobi);
+                      int slot_rho, int slot_rho_new, int first, int jacobi, double* x_deferred = nullptr, int slot_pap = 0);
 int launch_dot(pde_ctx* c, const Grid& g, int ncomp, const double* a, const double* b, int slot);
 int launch_zero(pde_ctx* c, const Grid& g, int ncomp, double* a);
 int launch_copy(pde_ctx* c, const Grid& g, int ncomp, double* dst, const double* src);

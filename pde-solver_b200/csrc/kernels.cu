@@ -387,6 +387,18 @@ k_cg_update_flat(double* __restrict__ x, double* __restrict__ r, const double* _
     double2* r2 = reinterpret_cast<double2*>(r + cidx * cs);
     const double2* p2 = reinterpret_cast<const double2*>(p + cidx * cs);
     const double2* q2 = reinterpret_cast<const double2*>(q + cidx * cs);
+    if (x == nullptr) {  // the x update rides on the p update of the same iteration (k_cg_pupdate_flat)
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        const double2 qv = q2[i];
+        double2 rv = r2[i];
+        rv.x = fma(-alpha, qv.x, rv.x);
+        rv.y = fma(-alpha, qv.y, rv.y);
+        r2[i] = rv;
+        rr = fma(rv.x, rv.x, rr);
+        rr = fma(rv.y, rv.y, rr);
+      }
+      continue;
+    }
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
       const double2 pv = p2[i], qv = q2[i];
       double2 xv = x2[i], rv = r2[i];
@@ -407,13 +419,36 @@ k_cg_update_flat(double* __restrict__ x, double* __restrict__ r, const double* _
 
 __global__ void __launch_bounds__(256)
 k_cg_pupdate_flat(double* __restrict__ p, const double* __restrict__ z, long long n, int ncomp, long long cs,
-                  const double* __restrict__ scal, int s_rho, int s_rho_new, int first) {
+                  const double* __restrict__ scal, int s_rho, int s_rho_new, int first, double* __restrict__ x,
+                  int s_pap) {
   double beta = 0.0;
   if (!first) {
     const double rho = scal[s_rho];
     beta = rho > 0.0 ? scal[s_rho_new] / rho : 0.0;
   }
   const long long n2 = n >> 1;
+  if (x != nullptr && !first) {
+    // deferred x update of this iteration, x += alpha p_old, on the way (p is read here anyway: 8 B/dof less
+    // traffic per iteration than updating x together with r)
+    const double pap = scal[s_pap], rho = scal[s_rho];
+    const double alpha = pap > 0.0 ? rho / pap : 0.0;
+    for (int cidx = 0; cidx < ncomp; ++cidx) {
+      double2* p2 = reinterpret_cast<double2*>(p + cidx * cs);
+      double2* x2 = reinterpret_cast<double2*>(x + cidx * cs);
+      const double2* z2 = reinterpret_cast<const double2*>(z + cidx * cs);
+      for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        const double2 zv = z2[i];
+        double2 pv = p2[i], xv = x2[i];
+        xv.x = fma(alpha, pv.x, xv.x);
+        xv.y = fma(alpha, pv.y, xv.y);
+        pv.x = fma(beta, pv.x, zv.x);
+        pv.y = fma(beta, pv.y, zv.y);
+        x2[i] = xv;
+        p2[i] = pv;
+      }
+    }
+    return;
+  }
   for (int cidx = 0; cidx < ncomp; ++cidx) {
     double2* p2 = reinterpret_cast<double2*>(p + cidx * cs);
     const double2* z2 = reinterpret_cast<const double2*>(z + cidx * cs);
@@ -448,11 +483,11 @@ int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, doub
 }
 
 int launch_cg_pupdate(pde_ctx* c, const Grid& g, const OpDev& op, double* p, const double* r_or_z, int slot_rho,
-                      int slot_rho_new, int first, int jacobi) {
+                      int slot_rho_new, int first, int jacobi, double* x_deferred, int slot_pap) {
   if (!jacobi) {
     int blocks = flat_blocks(c, g.total / 2, 256 * 2);
     k_cg_pupdate_flat<<<blocks, 256, 0, c->stream>>>(p, r_or_z, g.total, op.ncomp, g.comp_stride, c->scal, slot_rho,
-                                                     slot_rho_new, first);
+                                                     slot_rho_new, first, x_deferred, slot_pap);
     c->launches++;
     CUDA_OK(cudaGetLastError());
     return 0;

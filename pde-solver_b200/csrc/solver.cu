@@ -572,7 +572,8 @@ int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* 
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, w.p.p));
     PDE_OK(launch_stencil(c, g, A.bc, A.dev, a));
     if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 1));
-    PDE_OK(launch_cg_update(c, g, A.dev, x, r, w.p.p, w.q.p, sr, S_XY, sn, sn + 1, !gmg));
+    // GMG path: x += alpha p is deferred to the p update below (p is read there anyway)
+    PDE_OK(launch_cg_update(c, g, A.dev, gmg ? nullptr : x, r, w.p.p, w.q.p, sr, S_XY, sn, sn + 1, !gmg));
     if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 2));
     if (gmg) {
       bool fused = false;
@@ -580,7 +581,7 @@ int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* 
       if (!fused) PDE_OK(launch_dot(c, g, nc, r, z, sn));
       if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 1));
     }
-    PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, gmg ? z : r, sr, sn, 0, !gmg));
+    PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, gmg ? z : r, sr, sn, 0, !gmg, gmg ? x : nullptr, S_XY));
     ++it;
     if (trace && (it <= 30 || it % 50 == 0)) {
       double v[2], pap;
