@@ -275,6 +275,18 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
   }
   const long long col0 = (long long)g.PX * iy0 + ix;  // flat offset of (ix, iy0) inside a plane
   const unsigned col0u = (unsigned)col0;
+  // Everything the epilogue needs is static per thread except three plane-uniform cases (generic plane, Dirichlet
+  // z face, natural z face): row masks as 0/1 doubles, store masks as bit sets, the output column as a pointer.
+  //   generic plane : interior-class rows computed, rows on natural x/y faces left to k_face_rows (not stored)
+  //   Dirichlet face: every valid row stores 0
+  //   natural z face: every free row belongs to k_face_rows; only the x/y-Dirichlet rows store 0
+  double mgen[YS];
+#pragma unroll
+  for (int j = 0; j < YS; ++j) mgen[j] = ((slowxy >> j) & 1u) ? 0.0 : mrow[j];
+  const unsigned st_gen = valid & ~slowxy, st_zface = valid & ~freexy;
+  const bool has_y = a.y != nullptr;
+  double* const ycol = a.y + col0;   // never dereferenced when a.y is null
+  const long long pxb = g.PX;
 
   double accA[YS][NC], accB[YS][NC], accC[YS][NC];
   // own-column values of the resident plane; the plane read one step earlier is the one that retires
@@ -355,32 +367,28 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
       const bool ze0 = g.nc[2] > 0 && gz == 0, ze1 = g.nc[2] > 0 && gz == g.nzg - 1;
       const bool zout_dom = gz < 0 || gz > g.nzg - 1;   // ghost plane beyond the domain end: nothing lives there
       const bool zdir = zout_dom || (!z_excl && ((ze0 && bc.on[4]) || (ze1 && bc.on[5])));
-      const double mz = zdir ? 0.0 : 1.0;
-      unsigned todo = valid;
-      const unsigned slow = zdir ? 0u : ((ze0 || ze1) ? freexy : slowxy);
-      // plane base pointers are uniform over the CTA; per-thread offsets fit 32 bits
-      const long long pbase = (long long)g.plane * zout;
-      // rows on natural faces (incomplete element patches) are left to k_face_rows, launched right after
-      todo &= ~slow;
-      // interior-class rows: Dirichlet / out-of-range / face rows are masked by m = 0
+      const bool znat = !zdir && (ze0 || ze1);          // natural z face: all free rows go to k_face_rows
+      const double mz = (zdir || znat) ? 0.0 : 1.0;
+      const unsigned todo = has_y ? (zdir ? valid : (znat ? st_zface : st_gen)) : 0u;   // rows stored by this kernel
+      // plane base pointer: one 64-bit add per plane and component, rows by a running pointer
+      double* const yplane = ycol + (long long)g.plane * zout;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        double* yp = a.y ? a.y + pbase + c * g.comp_stride : nullptr;  // may alias xprev: no __restrict__
+        double* yp = yplane + c * g.comp_stride;  // may alias xprev: no __restrict__
         const double bB = a.bscale * a.bconst[c] * a.load_int;  // constant load term of the interior class
         const double c2d = a.c2 * a.dinv_int[c];
         const double s0d = a.s0 * a.dinv_int[c];
 #pragma unroll
         for (int j = 0; j < YS; ++j) {
           const bool on = (todo >> j) & 1u;
-          const double m = on ? mrow[j] * mz : 0.0;
-          const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
+          const double m = mgen[j] * mz;
           if (MODE == M_FIRST2) {
             // zero guess: x1 = d1 = s0 D^-1 b ; r = b - A x1 = b - s0 D^-1 (A b) ; d2 = c1 d1 + c2 D^-1 r
             const double bi = xv[j][c];
             const double d1 = s0d * bi;
             const double dn = m * fma(a.c1, d1, c2d * fma(-s0d, aP[j][c], bi));
             const double yv = m * d1 + dn;
-            if (on) yp[off] = yv;
+            if (on) *yp = yv;
             red_xy = fma(bi, yv, red_xy);
           } else if (CHEBY) {
             const double B = bv[j][c];
@@ -390,14 +398,15 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
                                : (a.prev_mode == 2 ? xo : (a.prev_mode == 3 ? xo - s0d * B : 0.0));
             const double dn = m * fma(a.c1, dprev, c2d * (B - aP[j][c]));
             const double yv = xo + dn;
-            if (on) yp[off] = yv;
+            if (on) *yp = yv;
             red_xy = fma(m * B, yv, red_xy);
           } else {
             const double yv = m * (HAS_B ? fma(a.ascale, aP[j][c], a.bscale * bv[j][c]) : fma(a.ascale, aP[j][c], bB));
-            if (on && yp) yp[off] = yv;
+            if (on) *yp = yv;
             red_xy = fma(xv[j][c], yv, red_xy);
             red_yy = fma(yv, yv, red_yy);
           }
+          yp += pxb;
         }
       }
     }
