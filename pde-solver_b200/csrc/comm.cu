@@ -102,7 +102,7 @@ int comm_allreduce_buf(pde_ctx* c, double* buf, size_t count) {
 }
 
 int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* f, int depth) {
-  if (c->world == 1) return 0;
+  if (c->world == 1 || g.nzl == g.nzg) return 0;   // single GPU, or a replicated (global) multigrid level
   if (depth < 1 || depth > PDE_NG) PDE_FAIL("halo depth out of range");
   if (depth > g.nzl) PDE_FAIL("halo deeper than the slab");
   const size_t n = (size_t)g.plane * depth;   // `depth` consecutive planes are contiguous

@@ -268,7 +268,7 @@ static int estimate_lmax(pde_ctx* c, MGLevel& L, int iters) {
     PDE_OK(launch_cheby_first(c, g, L.op.bc, L.op.dev, y, y, 1.0));  // y <- D^-1 y
     PDE_OK(launch_dot(c, g, nc, y, y, S_TMP0));
     PDE_OK(launch_dot(c, g, nc, x, x, S_TMP1));
-    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_TMP0, 2));
+    if (c->world > 1 && !L.replicated) PDE_OK(comm_allreduce_scal(c, S_TMP0, 2));
     double v[2];
     PDE_OK(read_scal(c, S_TMP0, 2, v));
     if (!(v[1] > 0.0) || !(v[0] > 0.0)) break;
@@ -299,10 +299,27 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
     Lu[q] = fine.g.h[ax[q]] * fine.g.nc[ax[q]];
   }
   const int ncomp = fine.tab.ncomp;
+  // Slab runs: a level whose GLOBAL grid is small is replicated on every rank (and so are all coarser ones).  Its
+  // right-hand side is assembled by one all-reduce of the restricted residual; the rest of the cycle below it runs
+  // without any communication, instead of three latency-bound halo exchanges per level.
+  static const long long rep_nodes = getenv("PDE_B200_REP_NODES") ? atoll(getenv("PDE_B200_REP_NODES")) : 400000;
+  bool replicate = false;
   for (int level = 0;; ++level) {
     std::unique_ptr<MGLevel> L(new MGLevel());
     Grid g;
-    PDE_OK(make_grid(dim, n, Lu, c->rank, c->world, &g));
+    if (c->world > 1 && level > 0 && !replicate) {
+      long long gn = 1;
+      for (int q = 0; q < nax; ++q) gn *= (n[q] + 1);
+      replicate = gn <= rep_nodes;
+    }
+    if (replicate) {
+      PDE_OK(make_grid(dim, n, Lu, 0, 1, &g));
+      PDE_OK(make_grid(dim, n, Lu, c->rank, c->world, &L->gslab));
+      L->gslab.comp_stride = g.comp_stride;   // a window into the replicated array: same pitch, rows and planes
+      L->replicated = true;
+    } else {
+      PDE_OK(make_grid(dim, n, Lu, c->rank, c->world, &g));
+    }
     if (kind == PDE_OP_ELASTICITY) PDE_OK(L->op.setup_elasticity(c, g, fine.bc, p0, p1));
     else PDE_OK(L->op.setup_scalar(c, g, fine.bc, p0, p1));
     PDE_OK(L->xa.alloc(c, g, ncomp));
@@ -325,7 +342,7 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
       if (nc2[q] < min_cells) can = false;
     }
     // slabs: the coarse partition must nest in the fine one (rank r owns coarse planes z0/2 ...)
-    if (c->world > 1 && n[nax - 1] % (2 * c->world) != 0) can = false;
+    if (c->world > 1 && !replicate && n[nax - 1] % (2 * c->world) != 0) can = false;
     if (can) {
       Grid gc;
       PDE_OK(make_grid(dim, nc2, Lu, 0, 1, &gc));  // global view: every rank takes the same decision
@@ -471,7 +488,7 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
   // needs an exchange of its own (3 exchanges per level and cycle instead of 6)
   std::vector<char> lean(nl, 0);
   for (int l = 0; l + 1 < nl; ++l)
-    lean[l] = c->world > 1 && nu == 2 && lv[l]->op.dev.uniform_diag && lv[l]->op.dev.ncomp == 1 && lv[l]->op.g.dim == 3 &&
+    lean[l] = c->world > 1 && !lv[l]->replicated && nu == 2 && lv[l]->op.dev.uniform_diag && lv[l]->op.dev.ncomp == 1 && lv[l]->op.g.dim == 3 &&
               lv[l]->op.g.nzl >= 8 && lv[l + 1]->op.g.nzl >= PDE_NG && sweep_applicable(lv[l]->op.g, 1) &&
               !getenv("PDE_B200_NO_POST2") && !getenv("PDE_B200_NO_LEAN_HALO");
   for (int l = 0; l < nl - 1; ++l) {
@@ -484,12 +501,23 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, cur[l], lean[l] ? PDE_NG : 1));
     PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
     if (c->world > 1 && !lean[l]) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, L.r.p));
-    PDE_OK(launch_restrict(c, L.op.g, lv[l + 1]->op.g, lv[l + 1]->op.bc, L.op.dev.ncomp, L.r.p, lv[l + 1]->b.p));
+    MGLevel& Lc = *lv[l + 1];
+    if (Lc.replicated && !L.replicated) {
+      // slab level -> replicated level: every rank restricts into its window of the global coarse array, the
+      // windows are disjoint, one all-reduce (sum with zeros) completes the array everywhere
+      const Grid& gc = Lc.op.g;
+      const int nc = L.op.dev.ncomp;
+      PDE_OK(launch_zero(c, gc, nc, Lc.b.p));
+      PDE_OK(launch_restrict(c, L.op.g, Lc.gslab, Lc.op.bc, nc, L.r.p, Lc.b.p + gc.plane * Lc.gslab.z0));
+      PDE_OK(comm_allreduce_buf(c, Lc.b.p, (size_t)(gc.comp_stride * (nc - 1) + gc.plane * gc.nzg)));
+    } else {
+      PDE_OK(launch_restrict(c, L.op.g, Lc.op.g, Lc.op.bc, L.op.dev.ncomp, L.r.p, Lc.b.p));
+    }
   }
   {
     MGLevel& L = *lv[nl - 1];
     const double* b = nl == 1 ? b0 : L.b.p;
-    if (L.n_dense > 0 && c->world == 1) {
+    if (L.n_dense > 0 && (c->world == 1 || L.replicated)) {
       PDE_OK(launch_dense_solve(c, L.n_dense, L.Ainv, L.idx, b, cur[nl - 1]));
     } else if (L.n_dense > 0) {
       PDE_OK(launch_dense_gather(c, L.n_dense, L.idx, b, L.bglob));

@@ -26,6 +26,10 @@ struct Operator {
 struct MGLevel {
   Operator op;
   Field b, xa, xb, r;
+  // slab runs: the level lives on its GLOBAL grid on every rank (no halo exchanges below the first such level);
+  // gslab is this rank's window of it (slab z range, global pitch), used when the level above restricts into it
+  bool replicated = false;
+  Grid gslab{};
   // coarsest level
   int n_dense = 0;
   double* Ainv = nullptr;
