@@ -728,7 +728,10 @@ static int launch_sweep_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDe
   sw.spec = SPEC ? 1 : 0;
   int txmax = tu.txmax > 0 ? tu.txmax : (NC == 1 ? 192 : 64);  // tuned on B200: heat 512^3, elasticity 1280x256x256
   txmax = txmax < 32 ? 32 : (txmax > 254 ? 254 : txmax);
-  if (txmax > (NC == 1 ? SW_MAXT1 : SW_MAXT3) - 34) txmax = (NC == 1 ? SW_MAXT1 : SW_MAXT3) - 34;
+  // room for the producer warp of the warp-specialised variant (and the even rounding of tx)
+  static const int txmargin = env_int("PDE_B200_SW_TXMARGIN", 2);   // 513 nodes: 3 tiles of 172 on 192 threads (A/B: apply 0.397 -> 0.375 ms)
+  const int margin = SPEC ? 34 : (txmargin < 2 ? 2 : txmargin);
+  if (txmax > (NC == 1 ? SW_MAXT1 : SW_MAXT3) - margin) txmax = (NC == 1 ? SW_MAXT1 : SW_MAXT3) - margin;
   sw.ntx = (g.nn[0] + txmax - 1) / txmax;
   sw.tx = (g.nn[0] + sw.ntx - 1) / sw.ntx;
   sw.tx += sw.tx & 1;  // even: the TMA box row must be a multiple of 16 bytes
