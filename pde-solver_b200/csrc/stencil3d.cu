@@ -286,6 +286,9 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
   const unsigned st_gen = valid & ~slowxy, st_zface = valid & ~freexy;
   const bool has_y = a.y != nullptr;
   double* const ycol = a.y + col0;   // never dereferenced when a.y is null
+  const double* const bcol0 = a.b + col0;       // likewise for a.b / a.xprev
+  const double* const dcol0 = a.xprev + col0;
+  const double* const xcol0 = a.x + col0;
   const long long pxb = g.PX;
 
   double accA[YS][NC], accB[YS][NC], accC[YS][NC];
@@ -307,19 +310,28 @@ k_sweep3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ Grid 
     // early global loads for the retiring outputs (consumed after the stencil arithmetic)
     double bv[YS][NC], dv[YS][NC], xv[YS][NC];
     if (FIN && (HAS_B || LOAD_D || !XQ_REG)) {
+      // column pointers of this thread at plane zout: one 64-bit add per array and plane, rows and components
+      // by running pointers (a full address rebuild per load costs ~6 instructions)
+      const long long pofs = (long long)g.plane * zout;
+      const bool use_d = LOAD_D && a.prev_mode == 1;
+      const double* bcol = HAS_B ? bcol0 + pofs : nullptr;
+      const double* dcol = use_d ? dcol0 + pofs : nullptr;
+      const double* xcol = xcol0 + pofs;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
-        const double* __restrict__ bp = HAS_B ? a.b + (long long)g.plane * zout + c * g.comp_stride : nullptr;
-        const double* dp = (LOAD_D && a.prev_mode == 1) ? a.xprev + (long long)g.plane * zout + c * g.comp_stride : nullptr;
-        const double* __restrict__ xp = a.x + (long long)g.plane * zout + c * g.comp_stride;
+        const double* bp = bcol;
+        const double* dp = dcol;
+        const double* xp = xcol;
 #pragma unroll
         for (int j = 0; j < YS; ++j) {
           const bool ok = (valid >> j) & 1u;
-          const unsigned off = col0u + (unsigned)j * (unsigned)g.PX;
-          if (HAS_B) bv[j][c] = ok ? bp[off] : 0.0;
-          if (LOAD_D) dv[j][c] = (ok && dp) ? dp[off] : 0.0;   // x_{k-1}
-          if (!XQ_REG) xv[j][c] = ok ? xp[off] : 0.0;
+          if (HAS_B) { bv[j][c] = ok ? *bp : 0.0; bp += pxb; }
+          if (LOAD_D) { dv[j][c] = (ok && use_d) ? *dp : 0.0; dp += pxb; }   // x_{k-1}
+          if (!XQ_REG) { xv[j][c] = ok ? *xp : 0.0; xp += pxb; }
         }
+        if (HAS_B) bcol += g.comp_stride;
+        if (LOAD_D) dcol += g.comp_stride;
+        xcol += g.comp_stride;
       }
     }
     if (FIN && XQ_REG) {
