@@ -78,6 +78,21 @@ k_stencil(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
 #pragma unroll
             for (int j = 0; j < NC; ++j) acc[i] = fma(ic.c[k][i * NC + j], xv[j], acc[i]);
         }
+      } else if (g.nk == 7 && cls == 13) {
+        // 2-D interior rows (internal axes x, z): the seven Kuhn offsets with constant-bank coefficients
+        constexpr int K2[7] = {0, 1, 2, 5, 6, 9, 10};
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const int k = K2[q];
+          const long long off = kOffDdev(k, g.PX, g.plane);
+          double xv[NC];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) xv[j] = a.x[idx + off + j * g.comp_stride];
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[i] = fma(ic.c[k][i * NC + j], xv[j], acc[i]);
+        }
       } else {
         for (int k = 0; k < g.nk; ++k) {
           const double* cf = coef + ((size_t)cls * PDE_NOFF + g.kidx[k]) * (NC * NC);
