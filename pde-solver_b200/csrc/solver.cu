@@ -602,12 +602,14 @@ int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* 
     if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 1));
     // GMG path: x += alpha p is deferred to the p update below (p is read there anyway)
     PDE_OK(launch_cg_update(c, g, A.dev, gmg ? nullptr : x, r, w.p.p, w.q.p, sr, S_XY, sn, sn + 1, !gmg));
-    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 2));
+    // slots (sn, sn+1) = (r.z, r.r): Jacobi fills both in the update kernel; with multigrid r.z only exists after
+    // the V-cycle, so the two partial sums travel in ONE all-reduce there (r.r is only needed by the poll below)
+    if (c->world > 1 && !gmg) PDE_OK(comm_allreduce_scal(c, sn, 2));
     if (gmg) {
       bool fused = false;
       PDE_OK(mg->vcycle(c, A, r, &z, sn, &fused));
       if (!fused) PDE_OK(launch_dot(c, g, nc, r, z, sn));
-      if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 1));
+      if (c->world > 1) PDE_OK(comm_allreduce_scal(c, sn, 2));
     }
     PDE_OK(launch_cg_pupdate(c, g, A.dev, w.p.p, gmg ? z : r, sr, sn, 0, !gmg, gmg ? x : nullptr, S_XY));
     ++it;
