@@ -115,6 +115,7 @@ def run_reference(args):
                                    "SciPy restatement, single-threaded"},
         "e2e": {"value": val, "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    args.emit_restore()
     print(json.dumps(out), flush=True)
     return 0
 
@@ -315,7 +316,9 @@ def run_native(args):
                 "serial_value": e2e_serial, "serial_steps": s_steps},
         "gpu_launches": int(st["launches"]), "clocks": clocks, "elasticity": elast, "halo": halo,
     }
+    args.emit_restore()
     print(json.dumps(out), flush=True)
+    os.dup2(2, 1)          # anything printed during teardown goes to stderr again
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -323,6 +326,25 @@ def run_native(args):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that chat on stdout (NCCL prints its version / debug lines there)
+    # are sent to stderr for the duration of the run, the result goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit_restore():
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+
+    rc = 1
+    try:
+        rc = _main(emit_restore)
+    finally:
+        sys.stdout.flush()
+    return rc
+
+
+def _main(emit_restore):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -337,6 +359,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
+    args.emit_restore = emit_restore
     if args.impl == "reference":
         return run_reference(args)
     return run_native(args)

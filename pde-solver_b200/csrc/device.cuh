@@ -29,6 +29,7 @@ struct pde_ctx {
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
   NcclApi* nccl = nullptr;
+  void* p2p = nullptr;        // peer-memory halo mailboxes (comm.cu), null until the first exchange
 };
 
 // ---- geometry helpers -----------------------------------------------------------------
@@ -234,3 +235,4 @@ int comm_allreduce_scal(pde_ctx* c, int slot, int count);
 // exchange `depth` (<= PDE_NG) boundary planes with the z-neighbours into the ghost planes
 int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* field, int depth = 1);
 int comm_allreduce_buf(pde_ctx* c, double* buf, size_t count);
+int comm_check_error(pde_ctx* c);   // fails if a peer-memory halo wait timed out

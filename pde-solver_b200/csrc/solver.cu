@@ -107,6 +107,7 @@ int read_scal(pde_ctx* c, int slot, int count, double* out) {
   k_publish_scal<<<1, 32, 0, c->stream>>>(c->scal + slot, c->h_scal_dev + slot, count);
   c->launches++;
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  if (c->world > 1) PDE_OK(comm_check_error(c));
   for (int i = 0; i < count; ++i) out[i] = ((volatile double*)c->h_scal)[slot + i];
   return 0;
 }
