@@ -248,7 +248,7 @@ def run_native(args):
                 "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "ms_per_launch": op_ms,
                 "per_gpu_dofs": op_nd, "nominal_8TBs_frac": ach / 8000.0}
 
-    # ---- halo exchange (N > 1): one 513x513 plane each way per z-neighbour, NCCL send/recv over NVLink ----
+    # ---- halo exchange (N > 1): one 513x513 plane each way per z-neighbour over NVLink ----
     halo = None
     if world > 1:
         barrier()
@@ -259,7 +259,9 @@ def run_native(args):
         halo = {"ms_per_exchange": h_ms, "plane_bytes": plane_bytes, "bytes_sent_per_rank_max": int(max_over_ranks(h_bytes)),
                 "gbs_per_direction": gbs, "nvlink_peer_copy_peak_gbs": 770.0,
                 "frac_of_nvlink": gbs / 770.0 if gbs else None,
-                "note": "grouped ncclSend/ncclRecv of one contiguous plane per neighbour; latency-bound at this size"}
+                "path": "nccl send/recv" if os.environ.get("PDE_B200_HALO") == "nccl" else
+                        "peer-memory mailbox kernel over NVLink (cudaIpc), NCCL send/recv as fallback",
+                "note": "one contiguous plane per neighbour; latency-bound at this size (flag round trips, not bytes)"}
 
     if rank != 0:
         if dist is not None:
