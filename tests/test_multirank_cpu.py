@@ -109,6 +109,7 @@ def test_reference_arm_under_torchrun_prints_once():
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1                      # rank 0 alone runs and prints
+    assert [l for l in r.stdout.splitlines() if l.strip()] == lines      # stdout carries the JSON line and nothing else
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
