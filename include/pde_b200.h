@@ -58,6 +58,9 @@ int pde_slab_partition(int dim, const int32_t n[3], int rank, int world, int lev
  * dim-D mesh; returns mean ms per exchange and the bytes this rank sends per exchange */
 int pde_halo_bench(pde_ctx* ctx, int dim, const int32_t n[3], int ncomp, int reps, double* ms_per_exchange,
                    int64_t* bytes_sent);
+/* self-check of the halo exchange (peer-memory kernel or NCCL): `reps` exchanges of `depth` planes of a field
+ * defined by the global node index; *mismatches = ghost entries that differ bitwise from the owner's values */
+int pde_halo_check(pde_ctx* ctx, int dim, const int32_t n[3], int ncomp, int depth, int reps, int64_t* mismatches);
 
 /* ---- meshes, dof maps, boundary sets (bit-exact rows a2-a4 of SURVEY §8) ------------- */
 /* IntervalMesh :229,1516 / RectangleMesh :369,1648 / BoxMesh :533,1803.

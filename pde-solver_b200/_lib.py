@@ -92,7 +92,7 @@ def lib():
                      "pde_nccl_unique_id", "pde_comm_init", "pde_mesh_counts", "pde_mesh_coords",
                      "pde_mesh_cells", "pde_dofmap_cells", "pde_boundary_mask", "pde_heat_solve",
                      "pde_heat_open", "pde_heat_set_state", "pde_heat_step", "pde_heat_get_state",
-                     "pde_heat_advance_batch",
+                     "pde_heat_advance_batch", "pde_halo_check",
                      "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench",
                      "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition", "pde_op_manufactured", "pde_halo_bench", "pde_wheat_solve",
                      "pde_mesh_coords_box"):
@@ -257,6 +257,13 @@ def op_solve(ctx, p, b, opts=None):
     o = opts if opts is not None else make_opts()
     check(lib().pde_op_solve(ctx.handle, C.byref(p), C.byref(o), ptr(b), ptr(x), C.byref(st)))
     return x, st.as_dict()
+
+
+def halo_check(ctx, dim, n, ncomp=1, depth=1, reps=4):
+    """Number of ghost entries that differ from the neighbours' values after `reps` exchanges (0 = correct)."""
+    bad = C.c_int64(0)
+    check(lib().pde_halo_check(ctx.handle, int(dim), i3(n), int(ncomp), int(depth), int(reps), C.byref(bad)))
+    return int(bad.value)
 
 
 def halo_bench(ctx, dim, n, ncomp=1, reps=50):

@@ -126,6 +126,46 @@ extern "C" int pde_halo_bench(pde_ctx* c, int dim, const int32_t n[3], int ncomp
   return 0;
 }
 
+// Halo exchange self-check: a field whose values depend on the GLOBAL node index is exchanged `reps` times with
+// `depth` planes (scaled by 2 and with the ghost planes wiped between repetitions, so stale or misplaced planes
+// show); *mismatches = number of ghost entries that differ bitwise from the owner's value.
+extern "C" int pde_halo_check(pde_ctx* c, int dim, const int32_t n[3], int ncomp, int depth, int reps,
+                              int64_t* mismatches) {
+  if (!c || !mismatches) PDE_FAIL("null argument");
+  if (ncomp < 1 || ncomp > 3) PDE_FAIL("ncomp must be 1..3");
+  if (depth < 1 || depth > PDE_NG) PDE_FAIL("depth out of range");
+  CUDA_OK(cudaSetDevice(c->device));
+  const double L1[3] = {1, 1, 1};
+  Grid g;
+  PDE_OK(make_grid(dim, n, L1, c->rank, c->world, &g));
+  Field f;
+  struct Rel { Field* f; ~Rel() { f->release(); } } rel{&f};
+  PDE_OK(f.alloc(c, g, ncomp));
+  DevMem bad;
+  PDE_OK(bad.alloc(sizeof(unsigned long long)));
+  CUDA_OK(cudaMemsetAsync(bad.p, 0, sizeof(unsigned long long), c->stream));
+  BcDev nobc;
+  std::memset(&nobc, 0, sizeof(nobc));
+  PDE_OK(launch_fill_pattern(c, g, nobc, ncomp, f.p));
+  double scale = 1.0;
+  for (int r = 0; r < reps; ++r) {
+    for (int i = 0; i < ncomp; ++i) {   // wipe the ghost planes
+      double* b = f.p + (size_t)i * g.comp_stride;
+      CUDA_OK(cudaMemsetAsync(b - (size_t)PDE_NG * g.plane, 0, sizeof(double) * PDE_NG * g.plane, c->stream));
+      CUDA_OK(cudaMemsetAsync(b + (size_t)g.nzl * g.plane, 0, sizeof(double) * PDE_NG * g.plane, c->stream));
+    }
+    PDE_OK(comm_halo_exchange(c, g, ncomp, f.p, depth));
+    PDE_OK(launch_halo_verify(c, g, ncomp, depth, f.p, scale, (unsigned long long*)bad.p));
+    PDE_OK(launch_axpy(c, g, ncomp, f.p, f.p, 1.0));   // f <- 2 f (owned planes; exact)
+    scale *= 2.0;
+  }
+  unsigned long long nb = 0;
+  PDE_OK(d2h(c, &nb, bad.p, sizeof(nb)));
+  if (c->world > 1) PDE_OK(comm_check_error(c));
+  *mismatches = (int64_t)nb;
+  return 0;
+}
+
 // ---- meshes -------------------------------------------------------------------------------------
 extern "C" int pde_mesh_coords(pde_ctx* c, int dim, const int32_t n[3], const double L[3], double* coords) {
   if (!c) PDE_FAIL("null context");

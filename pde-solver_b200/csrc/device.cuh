@@ -211,6 +211,8 @@ int launch_prolong_add(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& 
                        double* xf, int ghost = 0);
 // fields
 int launch_fill_ic(pde_ctx* c, const Grid& g, const BcDev& bc, double* u, double value, int apply_bc);
+int launch_halo_verify(pde_ctx* c, const Grid& g, int ncomp, int depth, const double* x, double scale,
+                       unsigned long long* bad);
 int launch_fill_pattern(pde_ctx* c, const Grid& g, const BcDev& bc, int ncomp, double* x);
 int launch_apply_bc_values(pde_ctx* c, const Grid& g, const BcDev& bc, double* u);
 int launch_pack(pde_ctx* c, const Grid& g, int ncomp, const double* padded, double* dense, int interleave);

@@ -831,6 +831,39 @@ int launch_fill_pattern(pde_ctx* c, const Grid& g, const BcDev& bc, int ncomp, d
   return 0;
 }
 
+// ghost planes after a halo exchange of `scale` * (the k_fill_pattern field without Dirichlet nodes): count the
+// entries that differ from the value the owning neighbour holds (bitwise: the scale is a power of two)
+__global__ void __launch_bounds__(128)
+k_halo_verify(const __grid_constant__ Grid g, int ncomp, int depth, const double* __restrict__ x, double scale,
+              unsigned long long* bad) {
+  const long long rows = (long long)g.nn[1] * 2 * depth;
+  unsigned long long nbad = 0;
+  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
+       row += (long long)gridDim.x * blockDim.y) {
+    const int iy = (int)(row % g.nn[1]);
+    const int q = (int)(row / g.nn[1]);                         // 0..depth-1 below, depth..2*depth-1 above
+    const int lz = q < depth ? -1 - q : g.nzl + (q - depth);
+    const int gz = lz + g.z0;
+    if (gz < 0 || gz > g.nzg - 1) continue;                     // no neighbour on that side
+    for (int ix = threadIdx.x; ix < g.nn[0]; ix += blockDim.x) {
+      const long long node = ((long long)gz * g.nn[1] + iy) * g.nn[0] + ix;
+      for (int i = 0; i < ncomp; ++i) {
+        const double want = scale * (sin(0.37 * (double)(node % 1000003) + i) + 0.5);
+        if (x[(long long)g.PX * iy + g.plane * lz + ix + i * g.comp_stride] != want) ++nbad;
+      }
+    }
+  }
+  if (nbad) atomicAdd(bad, nbad);
+}
+int launch_halo_verify(pde_ctx* c, const Grid& g, int ncomp, int depth, const double* x, double scale,
+                       unsigned long long* bad) {
+  RowLaunch rl = row_launch(c, g);
+  k_halo_verify<<<rl.grid, rl.block, 0, c->stream>>>(g, ncomp, depth, x, scale, bad);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_fill_ic(pde_ctx* c, const Grid& g, const BcDev& bc, double* u, double value, int apply_bc) {
   RowLaunch rl = row_launch(c, g);
   k_fill_ic<<<rl.grid, rl.block, 0, c->stream>>>(g, bc, u, value, 1, apply_bc);

@@ -93,6 +93,15 @@ for kind, mn, mL, faces in (("heat", [96, 40, 32 * world], [1.0, 0.5, 0.4 * worl
         print(f"[mgpu] manufactured {kind} {mn} x{world}: rel-L2 {err:.2e} iters {mst['iters_total']} levels {mst['levels']} "
               f"true relres {mst['true_relres']:.1e}", flush=True)
         ok = ok and err <= 1e-8 and mst["converged"] == 1 and mst["levels"] > 1
+# ---- halo exchange self-check: sizes grow (the mailboxes are re-mapped collectively), 1 / 2 planes, 1 / 3 components
+for n_h in ([40, 24, 16 * world], [96, 80, 24 * world], [512, 512, 8 * world]):
+    for ncomp_h, depth_h in ((1, 1), (1, 2), (3, 1), (3, 2)):
+        bad = _lib.halo_check(ctx, 3, n_h, ncomp_h, depth_h, reps=5)
+        flags = [None] * world
+        dist.all_gather_object(flags, bad)
+        assert sum(flags) == 0, f"halo exchange mismatches {flags} for n={n_h} ncomp={ncomp_h} depth={depth_h}"
+if rank == 0:
+    print(f"[mgpu] halo self-check ok ({os.environ.get('PDE_B200_HALO', 'peer-memory')} path)", flush=True)
 h_ms, h_bytes = _lib.halo_bench(ctx, 3, [512, 512, 64 * world], 1, reps=50)
 if rank == 0:
     print(f"[mgpu] halo exchange 513x513 plane: {h_ms * 1e3:.1f} us, {516 * 514 * 8 / (h_ms / 1e3) / 1e9:.0f} GB/s per direction",

@@ -294,11 +294,18 @@ def test_multi_gpu_slabs_match_oracle():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541",
-                        os.path.join(root, "scripts", "mgpu_check.py")], stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True, timeout=600, cwd=root)
-    assert r.returncode == 0 and "MGPU OK" in r.stdout, r.stdout[-3000:]
+    # both halo paths: the peer-memory mailbox kernel (default) and the NCCL send/recv fallback
+    for port, halo in ((29541, None), (29543, "nccl")):
+        env = dict(os.environ)
+        env.pop("PDE_B200_HALO", None)
+        if halo:
+            env["PDE_B200_HALO"] = halo
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port),
+                            os.path.join(root, "scripts", "mgpu_check.py")], stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=600, cwd=root, env=env)
+        assert r.returncode == 0 and "MGPU OK" in r.stdout, r.stdout[-3000:]
+        assert "halo self-check ok" in r.stdout
 
 
 # ---------------------------------------------------------------- pipelined batch of one-step advances
