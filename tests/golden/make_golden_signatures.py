@@ -9,7 +9,7 @@ import os
 import sys
 
 REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/fenics_mcp_server.py"
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden",
                    "reference_signatures.json")
 
 

@@ -1,7 +1,7 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        scripts/mgpu_check.py
+        tests/mgpu_check.py
 
 Slab-partitioned 3D heat (GMG-PCG and Jacobi-PCG) against the CPU oracle (<= 1e-8 rel-L2), plus an
 operator application against the oracle matrix.  Rank 0 prints 'MGPU OK'."""

@@ -1,5 +1,5 @@
 """Drop-in boundary: tool names / keyword arguments / defaults equal the reference's (golden JSON made by
-scripts/make_golden_signatures.py from /root/reference/fenics_mcp_server.py), the C-ABI library
+tests/golden/make_golden_signatures.py from /root/reference/fenics_mcp_server.py), the C-ABI library
 exports every symbol include/pde_b200.h declares, and (GPU) the tools work through MCP."""
 import asyncio
 import inspect

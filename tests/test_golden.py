@@ -1,4 +1,4 @@
-"""Committed golden vectors (tests/golden/oracle_vectors.npz, made by scripts/make_golden_vectors.py).
+"""Committed golden vectors (tests/golden/oracle_vectors.npz, made by tests/golden/make_golden_vectors.py).
 
 CPU: the oracle keeps reproducing them (integer arrays and coordinates bit-exact, solves to 1e-12).
 GPU: the CUDA path matches them (bit-exact for meshes / dof maps / boundary sets, <= 1e-8 rel-L2 for solves)."""

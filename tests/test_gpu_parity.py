@@ -302,7 +302,7 @@ def test_multi_gpu_slabs_match_oracle():
             env["PDE_B200_HALO"] = halo
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                             "--master-addr", "127.0.0.1", "--master-port", str(port),
-                            os.path.join(root, "scripts", "mgpu_check.py")], stdout=subprocess.PIPE,
+                            os.path.join(root, "tests", "mgpu_check.py")], stdout=subprocess.PIPE,
                            stderr=subprocess.STDOUT, text=True, timeout=600, cwd=root, env=env)
         assert r.returncode == 0 and "MGPU OK" in r.stdout, r.stdout[-3000:]
         assert "halo self-check ok" in r.stdout
