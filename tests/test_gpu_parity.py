@@ -383,3 +383,40 @@ def test_heat_3d_cylinder_and_composite_core(P, case):
     assert f.meta["geometry_type"] == case.get("geometry_type", "box")
     if "core_radius" in case:
         assert f.meta["base_diffusivity"] == kappa and "diffusivity" not in f.meta
+
+
+def test_heat_solve_pinned_snapshots_pipeline(P, ctx):
+    """pde_heat_solve with a PINNED values buffer: the snapshot downloads are truly asynchronous (copy stream, two
+    staging slots handed over by events) and overlap the following steps; every snapshot must still be the state
+    after exactly its step.  13 snapshots reuse each staging slot six times."""
+    import ctypes as C
+    L_ = P._lib
+    n, Ld, kappa, dt, steps, stride = [20, 12, 10], [1.0, 0.6, 0.5], 0.9, 0.01, 24, 2
+    ref = fo.solve_heat(3, Ld, n, kappa, T_initial=7.0, dt=dt, num_steps=steps, T_boundary=1.5,
+                        source_type="constant", source_value=4.0)
+    p = L_.HeatParams()
+    p.dim = 3
+    p.n = L_.i3(n)
+    p.L = L_.d3(Ld)
+    p.diffusivity, p.dt, p.num_steps, p.steady = kappa, dt, steps, 0
+    p.source_value = 4.0
+    p.initial_type = L_.IC["constant"]
+    p.snapshot_stride = stride
+    p.T_initial = 7.0
+    p.bc = P.mesh.heat_bc(3, T_boundary=1.5)
+    nv = ref.values.shape[1]
+    nsnap = 1 + steps // stride
+    buf = L_.PinnedArray(nsnap * nv)
+    times = np.empty(nsnap)
+    st = L_.Stats()
+    o = L_.make_opts(rtol=1e-10, precond="gmg")
+    try:
+        buf.array[:] = np.nan
+        L_.check(L_.lib().pde_heat_solve(ctx.handle, C.byref(p), C.byref(o), None, L_.ptr(buf.array), L_.ptr(times),
+                                         C.byref(st)))
+        vals = buf.array.reshape(nsnap, nv).copy()
+    finally:
+        buf.free()
+    assert np.allclose(times, ref.times[::stride], rtol=0, atol=1e-15)
+    for k in range(nsnap):
+        assert fo.rel_l2(vals[k], ref.values[k * stride]) <= TOL, k
