@@ -877,9 +877,128 @@ bool sweep_applicable(const Grid& g, int ncomp) {
   return true;
 }
 
+// ----------------------------------------------------------------------------------------------------
+// k_sweep2d: the 2-D heat / mass operators (internal axes x and z; rows are contiguous) with every face Dirichlet.
+//   A thread owns one column and marches over a chunk of rows keeping the three partial sums of the Kuhn 7-point
+//   stencil (centre, +-x, +-z, +-(x,z)) in registers, exactly like the plane march of k_sweep3d: row q contributes
+//   to outputs q-1, q and q+1, then output q-1 retires.  Three coalesced loads per row (the +-1 columns hit L1), no
+//   shared memory: DRAM sees every element once.  Same modes and epilogues as k_sweep3d<1, ., MODE>.
+// ----------------------------------------------------------------------------------------------------
+struct Coef2d {
+  double c0, cxp, cxm, czp, czm, cdp, cdm;   // offsets (0,0) (+1,0) (-1,0) (0,+1) (0,-1) (+1,+1) (-1,-1)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_sweep2d(const __grid_constant__ Grid g, const __grid_constant__ Coef2d C, const __grid_constant__ SweepArgs a,
+          int zc, int nbx, ReduceBuf red, double* red_out) {
+  constexpr bool CHEBY = MODE >= M_CHEBY;
+  constexpr bool HAS_B = MODE == M_RESID || MODE == M_CHEBY;
+  // 1-D grid (the block reduction indexes its partial sums by blockIdx.x): x block fastest
+  const int ix = (int)(blockIdx.x % nbx) * blockDim.x + threadIdx.x;
+  const int za = (int)(blockIdx.x / nbx) * zc;
+  const int zb = min(za + zc, g.nzl);
+  const bool col = ix < g.nn[0];
+  const double mx = (col && ix > 0 && ix < g.nn[0] - 1) ? 1.0 : 0.0;
+  const long long PX = g.PX;
+  // pads and ghost rows are zero (or hold the neighbour slab's rows), so the +-1 columns / rows need no guards;
+  // columns beyond the row stay inside the allocation (next row) and are masked
+  const double* xr = a.x + PX * (za - 1) + ix;
+  const double* br = HAS_B ? a.b + PX * za + ix : nullptr;
+  const bool use_d = MODE == M_CHEBY && a.prev_mode == 1;
+  const double* dr = use_d ? a.xprev + PX * za + ix : nullptr;
+  double* yr = a.y ? a.y + PX * za + ix : nullptr;
+  const double bB = a.bscale * a.bconst[0] * a.load_int;
+  const double c2d = a.c2 * a.dinv_int[0], s0d = a.s0 * a.dinv_int[0];
+  double accA = 0.0, accB = 0.0, xprev_own = 0.0;
+  double red_xy = 0.0, red_yy = 0.0;
+  for (int q = za - 1; q <= zb; ++q) {
+    const double vm = col ? xr[-1] : 0.0, v0 = col ? xr[0] : 0.0, vp = col ? xr[1] : 0.0;
+    xr += PX;
+    const double done = fma(C.cdp, vp, fma(C.czp, v0, accA));            // output row q-1 is complete
+    accA = fma(C.cxm, vm, fma(C.cxp, vp, fma(C.c0, v0, accB)));          // row q: in-row part on top of its dz=-1 part
+    accB = fma(C.cdm, vm, C.czm * v0);                                   // row q+1: dz=-1 part
+    if (q > za) {
+      const int z = q - 1;
+      const int gz = z + g.z0;
+      const double m = (gz > 0 && gz < g.nzg - 1) ? mx : 0.0;
+      const double xo = xprev_own;
+      double yv;
+      if (MODE == M_FIRST2) {
+        const double d1 = s0d * xo;
+        const double dn = m * fma(a.c1, d1, c2d * fma(-s0d, done, xo));
+        yv = m * d1 + dn;
+        red_xy = fma(xo, yv, red_xy);
+      } else if (CHEBY) {
+        const double B = col ? *br : 0.0;
+        const double dprev = a.prev_mode == 1 ? xo - (col ? *dr : 0.0)
+                           : (a.prev_mode == 2 ? xo : (a.prev_mode == 3 ? xo - s0d * B : 0.0));
+        const double dn = m * fma(a.c1, dprev, c2d * (B - done));
+        yv = xo + dn;
+        red_xy = fma(m * B, yv, red_xy);
+      } else {
+        const double B = HAS_B ? (col ? *br : 0.0) : 0.0;
+        yv = m * (HAS_B ? fma(a.ascale, done, a.bscale * B) : fma(a.ascale, done, bB));
+        red_xy = fma(xo, yv, red_xy);
+        red_yy = fma(yv, yv, red_yy);
+      }
+      if (col && yr) *yr = yv;
+      if (HAS_B) br += PX;
+      if (use_d) dr += PX;
+      if (yr) yr += PX;
+    }
+    xprev_own = v0;
+  }
+  if (a.do_reduce) {
+    if (CHEBY) { double v[1] = {red_xy}; block_reduce_finalize<1>(v, red, red_out); }
+    else { double v[2] = {red_xy, red_yy}; block_reduce_finalize<2>(v, red, red_out); }
+  }
+}
+
+static bool sweep2d_applicable(const Grid& g, const OpDev& op, const StencilArgs& a) {
+  static const int off = env_int("PDE_B200_NO_SWEEP2D", 0);
+  if (off) return false;
+  if (g.dim != 2 || g.nk != 7 || op.ncomp != 1 || !op.uniform_diag) return false;
+  if (g.nn[0] < 128 || g.nzl < 8) return false;           // small levels stay on the table kernel (launch bound anyway)
+  if (a.ghost_out) return false;
+  if (a.cheby == 1 && !a.b) return false;
+  return true;
+}
+
+template <int MODE>
+static int launch_sweep2d_t(pde_ctx* c, const Grid& g, const OpDev& op, const StencilArgs& a) {
+  Coef2d C;
+  C.c0 = op.h_int[0]; C.cxp = op.h_int[1]; C.cxm = op.h_int[2]; C.czp = op.h_int[5]; C.czm = op.h_int[6];
+  C.cdp = op.h_int[9]; C.cdm = op.h_int[10];
+  SweepArgs sa;
+  sa.x = a.x; sa.b = a.b; sa.y = a.y; sa.xprev = a.xprev; sa.prev_mode = a.prev_mode;
+  for (int i = 0; i < 3; ++i) sa.bconst[i] = a.bconst[i];
+  sa.bscale = a.bscale; sa.ascale = a.ascale; sa.c1 = a.c1; sa.c2 = a.c2; sa.s0 = a.s0;
+  sa.load_int = op.h_load_int;
+  for (int i = 0; i < 3; ++i) sa.dinv_int[i] = i < 1 ? op.h_dinv_int[i] : 0.0;
+  sa.do_reduce = a.reduce_slot_xy >= 0;
+  const int nbx = (g.nn[0] + 255) / 256;
+  int zc = env_int("PDE_B200_SW2D_ZC", 64);
+  zc = zc < 4 ? 4 : zc;
+  while (zc > 8 && (long long)nbx * ((g.nzl + zc - 1) / zc) < 4LL * c->sm_count) zc /= 2;
+  const int nbz = (g.nzl + zc - 1) / zc;
+  if ((long long)nbx * nbz > RED_MAX_BLOCKS) PDE_FAIL("2-D sweep grid exceeds the reduction buffer");
+  double* out = sa.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
+  k_sweep2d<MODE><<<(unsigned)(nbx * nbz), 256, 0, c->stream>>>(g, C, sa, zc, nbx, c->red, out);
+  c->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a,
                         bool* handled) {
   *handled = false;
+  if (sweep2d_applicable(g, op, a)) {
+    *handled = true;
+    if (a.cheby == 2) return launch_sweep2d_t<M_FIRST2>(c, g, op, a);
+    if (a.cheby) return launch_sweep2d_t<M_CHEBY>(c, g, op, a);
+    return a.b ? launch_sweep2d_t<M_RESID>(c, g, op, a) : launch_sweep2d_t<M_APPLY>(c, g, op, a);
+  }
   if (!sweep_applicable(g, op.ncomp)) return 0;
   const int ys = sweep_tune().ys;
   *handled = true;

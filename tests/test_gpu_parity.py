@@ -78,7 +78,9 @@ def _oracle_matrix(kind, dim, n, L, alpha, beta, lam, mu):
                                         # sizes that take the TMA plane-sweep kernel (several x/y tiles, z chunks)
                                         ("heat", 3, [70, 33, 40]), ("mass", 3, [64, 20, 9]),
                                         ("heat", 3, [400, 10, 8]), ("elasticity", 3, [66, 20, 12]),
-                                        ("elasticity", 3, [200, 9, 36])])
+                                        ("elasticity", 3, [200, 9, 36]),
+                                        # 2-D sizes that take the register-marching kernel when every face is Dirichlet
+                                        ("heat", 2, [300, 70]), ("mass", 2, [129, 200]), ("stiffness", 2, [256, 9])])
 def test_operator_apply_matches_oracle(P, ctx, kind, dim, n, variant):
     L = [1.0, 0.6, 0.35][:dim]
     alpha, beta = (1.0, 0.013) if kind == "heat" else ((1.0, 0.0) if kind == "mass" else (0.0, 1.0))
@@ -132,6 +134,22 @@ def test_heat_2d(P, precond):
     _check_heat(P, 2, [1.0, 0.5], [30, 18], okw,
                 dict(args=(1.0, 0.5, 30, 18, 0.5, 7.0, 5.0, 0.02, 4),
                      kw=dict(source_type="constant", source_value=30.0)), precond)
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "gmg"])
+def test_heat_2d_marching_kernel_sizes(P, precond):
+    """Grids wide enough for the register-marching 2-D sweep (k_sweep2d: >= 128 nodes across, all faces Dirichlet),
+    ragged against its 256-column blocks and 64-row chunks; with a source, non-zero boundary value and a steady solve."""
+    okw = dict(diffusivity=0.7, T_initial=3.0, dt=0.02, num_steps=4, T_boundary=2.0, source_type="constant",
+               source_value=9.0)
+    _check_heat(P, 2, [1.0, 0.4], [300, 70], okw,
+                dict(args=(1.0, 0.4, 300, 70, 0.7, 2.0, 3.0, 0.02, 4),
+                     kw=dict(source_type="constant", source_value=9.0)), precond)
+    okw = dict(diffusivity=1.3, T_initial=0.0, dt=0.01, num_steps=1, T_boundary=1.0, steady=True,
+               source_type="constant", source_value=5.0)
+    _check_heat(P, 2, [0.5, 1.0], [128, 96], okw,
+                dict(args=(0.5, 1.0, 128, 96, 1.3, 1.0, 0.0, 0.01, 1),
+                     kw=dict(steady=True, source_type="constant", source_value=5.0)), precond)
 
 
 @pytest.mark.parametrize("precond", ["jacobi", "gmg"])
