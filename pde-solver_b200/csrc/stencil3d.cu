@@ -903,51 +903,64 @@ k_sweep2d(const __grid_constant__ Grid g, const __grid_constant__ Coef2d C, cons
   const long long PX = g.PX;
   // pads and ghost rows are zero (or hold the neighbour slab's rows), so the +-1 columns / rows need no guards;
   // columns beyond the row stay inside the allocation (next row) and are masked
-  const double* xr = a.x + PX * (za - 1) + ix;
-  const double* br = HAS_B ? a.b + PX * za + ix : nullptr;
+  const double* xc = a.x + ix;                                   // column pointers at row 0
+  const double* bc_ = HAS_B ? a.b + ix : nullptr;
   const bool use_d = MODE == M_CHEBY && a.prev_mode == 1;
-  const double* dr = use_d ? a.xprev + PX * za + ix : nullptr;
-  double* yr = a.y ? a.y + PX * za + ix : nullptr;
+  const double* dc = use_d ? a.xprev + ix : nullptr;
+  double* yc = a.y ? a.y + ix : nullptr;                         // may alias xprev: rows are loaded before they are stored
   const double bB = a.bscale * a.bconst[0] * a.load_int;
   const double c2d = a.c2 * a.dinv_int[0], s0d = a.s0 * a.dinv_int[0];
   double accA = 0.0, accB = 0.0, xprev_own = 0.0;
   double red_xy = 0.0, red_yy = 0.0;
-  for (int q = za - 1; q <= zb; ++q) {
-    const double vm = col ? xr[-1] : 0.0, v0 = col ? xr[0] : 0.0, vp = col ? xr[1] : 0.0;
-    xr += PX;
-    const double done = fma(C.cdp, vp, fma(C.czp, v0, accA));            // output row q-1 is complete
-    accA = fma(C.cxm, vm, fma(C.cxp, vp, fma(C.c0, v0, accB)));          // row q: in-row part on top of its dz=-1 part
-    accB = fma(C.cdm, vm, C.czm * v0);                                   // row q+1: dz=-1 part
-    if (q > za) {
-      const int z = q - 1;
-      const int gz = z + g.z0;
-      const double m = (gz > 0 && gz < g.nzg - 1) ? mx : 0.0;
-      const double xo = xprev_own;
-      double yv;
-      if (MODE == M_FIRST2) {
-        const double d1 = s0d * xo;
-        const double dn = m * fma(a.c1, d1, c2d * fma(-s0d, done, xo));
-        yv = m * d1 + dn;
-        red_xy = fma(xo, yv, red_xy);
-      } else if (CHEBY) {
-        const double B = col ? *br : 0.0;
-        const double dprev = a.prev_mode == 1 ? xo - (col ? *dr : 0.0)
-                           : (a.prev_mode == 2 ? xo : (a.prev_mode == 3 ? xo - s0d * B : 0.0));
-        const double dn = m * fma(a.c1, dprev, c2d * (B - done));
-        yv = xo + dn;
-        red_xy = fma(m * B, yv, red_xy);
-      } else {
-        const double B = HAS_B ? (col ? *br : 0.0) : 0.0;
-        yv = m * (HAS_B ? fma(a.ascale, done, a.bscale * B) : fma(a.ascale, done, bB));
-        red_xy = fma(xo, yv, red_xy);
-        red_yy = fma(yv, yv, red_yy);
-      }
-      if (col && yr) *yr = yv;
-      if (HAS_B) br += PX;
-      if (use_d) dr += PX;
-      if (yr) yr += PX;
+  constexpr int U = 4;   // rows per step: all loads of a step are issued before its arithmetic and stores
+  for (int q0 = za - 1; q0 <= zb; q0 += U) {
+    double vm[U], v0[U], vp[U], Bv[U], Dv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u;
+      const bool ok = col && q <= zb;
+      const double* p = xc + PX * q;
+      vm[u] = ok ? p[-1] : 0.0;
+      v0[u] = ok ? p[0] : 0.0;
+      vp[u] = ok ? p[1] : 0.0;
+      const bool rz = ok && q > za;                              // output row z = q-1 retires at this row
+      Bv[u] = (HAS_B && rz) ? bc_[PX * (q - 1)] : 0.0;
+      Dv[u] = (use_d && rz) ? dc[PX * (q - 1)] : 0.0;
     }
-    xprev_own = v0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int q = q0 + u;
+      if (q > zb) break;
+      const double done = fma(C.cdp, vp[u], fma(C.czp, v0[u], accA));          // output row q-1 is complete
+      accA = fma(C.cxm, vm[u], fma(C.cxp, vp[u], fma(C.c0, v0[u], accB)));      // row q: in-row part on top of its dz=-1 part
+      accB = fma(C.cdm, vm[u], C.czm * v0[u]);                                  // row q+1: dz=-1 part
+      if (q > za) {
+        const int z = q - 1;
+        const int gz = z + g.z0;
+        const double m = (gz > 0 && gz < g.nzg - 1) ? mx : 0.0;
+        const double xo = xprev_own;
+        double yv;
+        if (MODE == M_FIRST2) {
+          const double d1 = s0d * xo;
+          const double dn = m * fma(a.c1, d1, c2d * fma(-s0d, done, xo));
+          yv = m * d1 + dn;
+          red_xy = fma(xo, yv, red_xy);
+        } else if (CHEBY) {
+          const double B = Bv[u];
+          const double dprev = a.prev_mode == 1 ? xo - Dv[u]
+                             : (a.prev_mode == 2 ? xo : (a.prev_mode == 3 ? xo - s0d * B : 0.0));
+          const double dn = m * fma(a.c1, dprev, c2d * (B - done));
+          yv = xo + dn;
+          red_xy = fma(m * B, yv, red_xy);
+        } else {
+          yv = m * (HAS_B ? fma(a.ascale, done, a.bscale * Bv[u]) : fma(a.ascale, done, bB));
+          red_xy = fma(xo, yv, red_xy);
+          red_yy = fma(yv, yv, red_yy);
+        }
+        if (col && yc) yc[PX * z] = yv;
+      }
+      xprev_own = v0[u];
+    }
   }
   if (a.do_reduce) {
     if (CHEBY) { double v[1] = {red_xy}; block_reduce_finalize<1>(v, red, red_out); }
