@@ -57,6 +57,24 @@ for precond in ("gmg", "jacobi"):
         print(f"[mgpu] heat {n} x{world} {precond}: rel-L2 {err:.2e} iters {st['iters_total']} levels {st['levels']} "
               f"converged {st['converged']}", flush=True)
         ok = ok and err <= 1e-8 and st["converged"] == 1 and (precond == "jacobi" or st["levels"] > 1)
+# ---- 2-D heat, slabs along y (internal z): wide enough for the register-marching kernel k_sweep2d ----
+n2, L2 = [192, 48 * world], [1.0, 0.5 * world]
+ref2 = fo.solve_heat(2, L2, n2, 0.8, T_initial=6.0, dt=0.02, num_steps=3, T_boundary=1.0, source_type="constant",
+                     source_value=3.0) if rank == 0 else None
+for precond in ("gmg", "jacobi"):
+    bc2 = _lib.make_bc({f: 1.0 for f in range(4)})
+    hs = _lib.HeatStepper(ctx, 2, n2, L2, 0.8, 0.02, T_initial=6.0, bc=bc2, source_value=3.0,
+                          opts=_lib.make_opts(rtol=1e-10, precond=precond))
+    st = hs.step(3)
+    u = np.empty(hs.nloc)
+    hs.get_state(u)
+    hs.close()
+    full = gather(u)
+    if rank == 0:
+        err = fo.rel_l2(full, ref2.values[-1])
+        print(f"[mgpu] heat 2-D {n2} x{world} {precond}: rel-L2 {err:.2e} iters {st['iters_total']} levels {st['levels']}",
+              flush=True)
+        ok = ok and err <= 1e-8 and st["converged"] == 1
 # ---- elasticity: cantilever under gravity, slab-partitioned GMG-PCG + von Mises projection (C ABI, local slabs) ----
 import ctypes as C
 en, eL = [16, 4, 4 * world * 2], [1.0, 0.25, 0.5 * world]
