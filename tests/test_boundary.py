@@ -208,3 +208,39 @@ def test_streaming_solve_matches_in_memory(server, tmp_path, monkeypatch):
     assert res.meta["snapshots_file"].endswith(".xdmf")
     t, v = io.read_xdmf_series(res.meta["snapshots_file"])
     assert v.shape == (4, 81)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in _lib.py and the structs of include/pde_b200.h (compiled here as plain C99) agree in size
+    and in the offsets of the fields behind which padding can hide."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from pde_solver_b200 import _lib as L
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    pairs = dict(pde_bc="Bc", pde_solver_opts="SolverOpts", pde_stats="Stats", pde_heat_params="HeatParams",
+                 pde_wheat_params="WheatParams", pde_elast_params="ElastParams", pde_op_params="OpParams")
+    offs = [("pde_wheat_params", "bc"), ("pde_wheat_params", "weight_kind"), ("pde_wheat_params", "core_radius"),
+            ("pde_wheat_params", "initial_wavenumber"), ("pde_heat_params", "bc"), ("pde_heat_params", "T_initial"),
+            ("pde_op_params", "variant"), ("pde_elast_params", "quantity"), ("pde_elast_params", "area"),
+            ("pde_stats", "final_relres"), ("pde_solver_opts", "cheby_ratio")]
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "pde_b200.h"', "int main(void) {"]
+    for cname in pairs:
+        src.append(f'  printf("S {cname} %zu\\n", sizeof({cname}));')
+    for cname, fld in offs:
+        src.append(f'  printf("O {cname} {fld} %zu\\n", offsetof({cname}, {fld}));')
+    src += ["  return 0;", "}"]
+    cfile = tmp_path / "abi.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path / "abi"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(cfile), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split("\n")
+    for line in filter(None, out):
+        t = line.split()
+        if t[0] == "S":
+            assert C.sizeof(getattr(L, pairs[t[1]])) == int(t[2]), line
+        else:
+            assert getattr(getattr(L, pairs[t[1]]), t[2]).offset == int(t[3]), line
