@@ -371,6 +371,10 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
 }
 
 void Hierarchy::release() {
+  if (gexec) cudaGraphExecDestroy(gexec);
+  gexec = nullptr;
+  gstate = 0;
+  gnodes = 0;
   for (auto& L : lv) {
     L->op.release();
     L->b.release(); L->xa.release(); L->xb.release(); L->r.release();
@@ -492,7 +496,8 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
     lean[l] = c->world > 1 && !lv[l]->replicated && nu == 2 && lv[l]->op.dev.uniform_diag && lv[l]->op.dev.ncomp == 1 && lv[l]->op.g.dim == 3 &&
               lv[l]->op.g.nzl >= 8 && lv[l + 1]->op.g.nzl >= PDE_NG && sweep_applicable(lv[l]->op.g, 1) &&
               !getenv("PDE_B200_NO_POST2") && !getenv("PDE_B200_NO_LEAN_HALO");
-  for (int l = 0; l < nl - 1; ++l) {
+  // down: pre-smoothing and residual of level l, restriction into level l+1
+  auto down = [&](int l) -> int {
     MGLevel& L = *lv[l];
     const double* b = l == 0 ? b0 : L.b.p;
     PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, true, ratio));   // exchanges one halo plane of b (fused first sweeps)
@@ -501,6 +506,10 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
     a.ghost_out = lean[l];
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, cur[l], lean[l] ? PDE_NG : 1));
     PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
+    return 0;
+  };
+  auto restrict_to = [&](int l) -> int {   // level l -> l+1
+    MGLevel& L = *lv[l];
     if (c->world > 1 && !lean[l]) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, L.r.p));
     MGLevel& Lc = *lv[l + 1];
     if (Lc.replicated && !L.replicated) {
@@ -514,8 +523,9 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
     } else {
       PDE_OK(launch_restrict(c, L.op.g, Lc.op.g, Lc.op.bc, L.op.dev.ncomp, L.r.p, Lc.b.p));
     }
-  }
-  {
+    return 0;
+  };
+  auto coarsest = [&]() -> int {
     MGLevel& L = *lv[nl - 1];
     const double* b = nl == 1 ? b0 : L.b.p;
     if (L.n_dense > 0 && (c->world == 1 || L.replicated)) {
@@ -527,15 +537,65 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
     }
     else PDE_OK(smooth(c, L, b, &cur[nl - 1], &oth[nl - 1], nl == 1 ? nu : coarse_sweeps, true, nl == 1 ? ratio : 30.0,
                        nl == 1 ? dot_slot : -1, nl == 1 ? dot_done : nullptr));
-  }
-  for (int l = nl - 2; l >= 0; --l) {
+    return 0;
+  };
+  auto prolong_into = [&](int l) -> int {   // level l+1 -> l
     MGLevel& L = *lv[l];
-    const double* b = l == 0 ? b0 : L.b.p;
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, lv[l + 1]->op.g, L.op.dev.ncomp, cur[l + 1], lean[l] ? PDE_NG : 1));
     PDE_OK(launch_prolong_add(c, L.op.g, lv[l + 1]->op.g, L.op.bc, L.op.dev.ncomp, cur[l + 1], cur[l], lean[l] ? PDE_NG : 0));
+    return 0;
+  };
+  auto post = [&](int l) -> int {
+    MGLevel& L = *lv[l];
+    const double* b = l == 0 ? b0 : L.b.p;
     PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, false, ratio, l == 0 ? dot_slot : -1, l == 0 ? dot_done : nullptr,
                   lean[l] != 0));
+    return 0;
+  };
+  // the part below level 0: fixed kernels, fixed arguments
+  auto middle = [&]() -> int {
+    PDE_OK(restrict_to(0));
+    for (int l = 1; l < nl - 1; ++l) { PDE_OK(down(l)); PDE_OK(restrict_to(l)); }
+    PDE_OK(coarsest());
+    for (int l = nl - 2; l >= 1; --l) { PDE_OK(prolong_into(l)); PDE_OK(post(l)); }
+    PDE_OK(prolong_into(0));
+    return 0;
+  };
+  if (nl == 1) {
+    PDE_OK(coarsest());
+    *z_out = cur[0];
+    return 0;
   }
+  static const int graph_env = getenv("PDE_B200_MG_GRAPH") ? atoi(getenv("PDE_B200_MG_GRAPH")) : 1;
+  if (gstate == 0 && !(graph_env && c->world == 1 && nl >= 3)) gstate = -1;
+  PDE_OK(down(0));
+  if (gstate == 2) {
+    CUDA_OK(cudaGraphLaunch(gexec, c->stream));
+    c->launches += gnodes;
+  } else if (gstate == 1) {
+    // second cycle: every static set-up (function attributes, tensor maps) happened in the first one
+    const long long l0 = c->launches;
+    CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = middle();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ec = cudaStreamEndCapture(c->stream, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ec != cudaSuccess || !graph) { cudaGetLastError(); gstate = -1; PDE_OK(middle()); }
+    else {
+      gnodes = c->launches - l0;
+      const cudaError_t ei = cudaGraphInstantiate(&gexec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ei != cudaSuccess) { cudaGetLastError(); gexec = nullptr; gstate = -1; c->launches = l0; PDE_OK(middle()); }
+      else {
+        gstate = 2;
+        CUDA_OK(cudaGraphLaunch(gexec, c->stream));   // the capture did not execute anything
+      }
+    }
+  } else {
+    PDE_OK(middle());
+    if (gstate == 0) gstate = 1;
+  }
+  PDE_OK(post(0));
   *z_out = cur[0];
   return 0;
 }

@@ -50,6 +50,12 @@ struct Hierarchy {
              bool* dot_done = nullptr);
   int levels() const { return (int)lv.size(); }
   void release();
+  // single-GPU runs: everything between the level-0 residual and the level-0 post-smoother (restriction, levels
+  // 1.., coarsest solve, prolongation into level 0) is a fixed sequence of small kernels with fixed arguments; it is
+  // captured into a CUDA graph on the second cycle and replayed afterwards (launch-bound on the coarse levels)
+  cudaGraphExec_t gexec = nullptr;
+  int gstate = 0;            // 0: no cycle yet, 1: one live cycle done (static set-up complete), 2: graph ready, -1: off
+  long long gnodes = 0;      // kernels inside the graph (for the launch count)
 };
 
 struct PcgWork {
