@@ -438,3 +438,58 @@ def test_heat_solve_pinned_snapshots_pipeline(P, ctx):
     assert np.allclose(times, ref.times[::stride], rtol=0, atol=1e-15)
     for k in range(nsnap):
         assert fo.rel_l2(vals[k], ref.values[k * stride]) <= TOL, k
+
+
+# ---------------------------------------------------------------- Fourier symbol of the interior stencil (SURVEY 8c iv-b)
+def _symbol(dim, h, alpha, beta, theta):
+    """sum_d w_d exp(i theta.d) of alpha*M + beta*K on the Kuhn / right-diagonal P1 mesh, from the closed-form weights
+    (SURVEY A.2): independent of the oracle's assembly code."""
+    if dim == 3:
+        hx, hy, hz = h
+        vol = hx * hy * hz
+        kx, ky, kz = hy * hz / hx, hx * hz / hy, hx * hy / hz
+        w = {(0, 0, 0): alpha * vol * 2 / 5 + beta * 2 * (kx + ky + kz)}
+        for d, k in (((1, 0, 0), kx), ((0, 1, 0), ky), ((0, 0, 1), kz)):
+            w[d] = alpha * vol / 20 - beta * k
+        for d in ((1, 1, 0), (1, 0, 1), (0, 1, 1)):
+            w[d] = alpha * vol / 30
+        w[(1, 1, 1)] = alpha * vol / 20
+    else:
+        hx, hy = h
+        vol = hx * hy
+        w = {(0, 0): alpha * vol / 2 + beta * 2 * (hy / hx + hx / hy),
+             (1, 0): alpha * vol / 12 - beta * hy / hx, (0, 1): alpha * vol / 12 - beta * hx / hy,
+             (1, 1): alpha * vol / 12}
+    zero = tuple([0] * dim)
+    C = w[zero]
+    for d, v in w.items():
+        if d != zero:
+            C += 2 * v * np.cos(np.dot(theta, d))          # the stencil is symmetric: w(-d) = w(d), the sine parts cancel
+    return C, max(abs(v) for v in w.values())
+
+
+@pytest.mark.parametrize("dim,n,L,faces", [(3, [512, 512, 512], [1.0, 1.0, 1.0], range(6)),          # config 4, TMA sweep
+                                           (3, [320, 64, 64], [1.0, 0.2, 0.2], []),                   # config 3 grid, no BC
+                                           (2, [4096, 4096], [1.0, 1.0], range(4)),                   # config 2, k_sweep2d
+                                           (2, [300, 70], [1.0, 0.4], [])])                           # 2-D table kernel
+def test_interior_rows_have_the_closed_form_fourier_symbol(P, ctx, dim, n, L, faces):
+    """x = cos(theta.n + phi) is an eigenvector of the interior stencil with the eigenvalue sum_d w_d cos(theta.d):
+    checked at the BASELINE sizes on every row whose patch is complete, against closed-form weights."""
+    alpha, beta = 1.0, 0.01
+    theta = np.array([0.31, 0.73, 1.17][:dim])
+    nn = [k + 1 for k in n]
+    ax = [np.arange(k, dtype=np.float64) for k in nn]
+    phase = 0.4 + theta[0] * ax[0][None, :]                 # natural order: x fastest
+    if dim == 2:
+        phase = phase + theta[1] * ax[1][:, None]
+    else:
+        phase = phase[None, :, :] + theta[1] * ax[1][None, :, None] + theta[2] * ax[2][:, None, None]
+    x = np.cos(phase)
+    del phase
+    h = [Lk / k for Lk, k in zip(L, n)]
+    C, wmax = _symbol(dim, h, alpha, beta, theta)
+    p = P._lib.op_params("heat", dim, n, L, alpha, beta, bc=P._lib.make_bc({f: 0.0 for f in faces}) if faces else None)
+    y = P._lib.op_apply(ctx, p, x.reshape(1, -1)).reshape(x.shape)
+    inner = tuple([slice(1, -1)] * dim)
+    err = np.abs(y[inner] - C * x[inner]).max()
+    assert err <= 1e-12 * 15 * wmax, (err, wmax)

@@ -209,3 +209,36 @@ def test_special_3d_core_marks_cells_by_vertices_and_midpoint():
                                   core_radius=0.6, core_diffusivity=50.0)
     f1 = fo.solve_heat_3d_special(1.0, 1.0, 1.0, [2, 4, 4], 1.0, T_initial=3.0, dt=0.05, num_steps=2)
     assert np.abs(f0.values[-1] - f1.values[-1]).max() > 1e-3      # the core changes the solution
+
+
+# ---------------------------------------------------------------- (iv-b) Fourier symbol of the interior stencil
+@pytest.mark.parametrize("dim,n,L", [(3, [6, 5, 7], [1.0, 0.6, 0.35]), (2, [7, 6], [1.0, 0.4]), (3, [4, 4, 4], [1, 1, 1])])
+def test_assembled_interior_rows_have_the_closed_form_symbol(dim, n, L):
+    """cos(theta.n + phi) is an eigenvector of the interior rows of alpha*M + beta*K with eigenvalue
+    sum_d w_d cos(theta.d), w_d the closed-form Kuhn / right-diagonal P1 weights (mass 2/5, 1/20, 1/30,
+    1/20 and the 7-point Laplacian in 3-D; 1/2, 1/12 and the 5-point Laplacian in 2-D)."""
+    alpha, beta = 1.0, 0.01
+    theta = np.array([0.31, 0.73, 1.17][:dim])
+    h = [a / b for a, b in zip(L, n)]
+    if dim == 3:
+        hx, hy, hz = h
+        vol, kx, ky, kz = hx * hy * hz, hy * hz / hx, hx * hz / hy, hx * hy / hz
+        w = {(0, 0, 0): alpha * vol * 2 / 5 + beta * 2 * (kx + ky + kz), (1, 0, 0): alpha * vol / 20 - beta * kx,
+             (0, 1, 0): alpha * vol / 20 - beta * ky, (0, 0, 1): alpha * vol / 20 - beta * kz,
+             (1, 1, 0): alpha * vol / 30, (1, 0, 1): alpha * vol / 30, (0, 1, 1): alpha * vol / 30,
+             (1, 1, 1): alpha * vol / 20}
+    else:
+        hx, hy = h
+        vol = hx * hy
+        w = {(0, 0): alpha * vol / 2 + beta * 2 * (hy / hx + hx / hy), (1, 0): alpha * vol / 12 - beta * hy / hx,
+             (0, 1): alpha * vol / 12 - beta * hx / hy, (1, 1): alpha * vol / 12}
+    zero = tuple([0] * dim)
+    C = w[zero] + sum(2 * v * np.cos(np.dot(theta, d)) for d, v in w.items() if d != zero)
+    m = fo.make_mesh(dim, L, n)
+    K, M = fo.assemble_stiffness_mass(m)
+    A = (alpha * M + beta * K).tocsr()
+    nn = [k + 1 for k in n]
+    idx = np.indices(nn[::-1]).reshape(dim, -1)[::-1]           # natural order, x fastest
+    x = np.cos(0.4 + sum(theta[d] * idx[d] for d in range(dim)))
+    interior = np.all([(idx[d] > 0) & (idx[d] < nn[d] - 1) for d in range(dim)], axis=0)
+    assert np.abs((A @ x)[interior] - C * x[interior]).max() <= 1e-14 * max(abs(v) for v in w.values())
