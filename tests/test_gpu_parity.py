@@ -493,3 +493,47 @@ def test_interior_rows_have_the_closed_form_fourier_symbol(P, ctx, dim, n, L, fa
     inner = tuple([slice(1, -1)] * dim)
     err = np.abs(y[inner] - C * x[inner]).max()
     assert err <= 1e-12 * 15 * wmax, (err, wmax)
+
+
+# ---------------------------------------------------------------- size-independent operator properties at BASELINE sizes
+@pytest.mark.parametrize("n", [[320, 64, 64], [1280, 256, 256]])
+def test_elasticity_annihilates_linear_displacements_at_full_size(P, ctx, n):
+    """Patch test on the GPU at the sizes of configs 3 and 5: a displacement field with a constant gradient (rigid
+    motions included) has constant stress, so every row whose element patch is complete gives zero."""
+    L = [1.0, 0.2, 0.2]
+    lam, mu = fo.lame(210e9, 0.3, 3)
+    nn = [k + 1 for k in n]
+    xs = [np.linspace(0.0, Lk, k) for Lk, k in zip(L, nn)]
+    G = np.array([[0.3, -1.1, 0.7], [0.9, 0.2, -0.4], [-0.6, 0.5, 1.3]])
+    a0 = np.array([0.25, -0.5, 0.75])
+    u = np.empty((3, nn[2], nn[1], nn[0]))
+    for i in range(3):
+        u[i] = a0[i] + G[i, 0] * xs[0][None, None, :] + G[i, 1] * xs[1][None, :, None] + G[i, 2] * xs[2][:, None, None]
+    p = P._lib.op_params("elasticity", 3, n, L, lam=lam, mu=mu)
+    scale = np.abs(P._lib.op_table(p)).max() * np.abs(u).max()
+    y = P._lib.op_apply(ctx, p, u.reshape(3, -1)).reshape(u.shape)
+    assert np.abs(y[:, 1:-1, 1:-1, 1:-1]).max() <= 1e-12 * scale
+    assert np.abs(y).max() > 1e-6 * scale          # the traction rows on the faces are not zero
+
+
+@pytest.mark.parametrize("kind,n,L,faces", [("heat", [512, 512, 512], [1.0, 1.0, 1.0], range(6)),
+                                            ("elasticity", [640, 128, 128], [1.0, 0.2, 0.2], [0]),
+                                            ("heat", [4096, 4096], [1.0, 1.0], range(4))])
+def test_operator_is_symmetric_at_full_size(P, ctx, kind, n, L, faces):
+    """x.(A y) = y.(A x) for random x, y that vanish on the Dirichlet nodes: symmetry of the matrix-free operator
+    including its natural-face rows (k_face_rows) and the masked Dirichlet rows."""
+    dim = len(n)
+    nc = dim if kind == "elasticity" else 1
+    lam, mu = fo.lame(210e9, 0.3, 3)
+    bc = P._lib.make_bc({f: 0.0 for f in faces})
+    mask, _ = P.mesh.dirichlet(dim, n, bc)
+    free = (~mask.astype(bool)).astype(np.float64)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((nc, free.size)) * free
+    y = rng.standard_normal((nc, free.size)) * free
+    p = P._lib.op_params(kind, dim, n, L, 1.0, 0.01, lam, mu, bc=bc)
+    Ax = P._lib.op_apply(ctx, p, x)
+    Ay = P._lib.op_apply(ctx, p, y)
+    a, b = float(np.vdot(y, Ax)), float(np.vdot(x, Ay))
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b), float(np.linalg.norm(x) * np.linalg.norm(Ay)))
+    assert float(np.vdot(x, Ax)) > 0.0               # positive definite on the free dofs
