@@ -537,3 +537,36 @@ def test_operator_is_symmetric_at_full_size(P, ctx, kind, n, L, faces):
     a, b = float(np.vdot(y, Ax)), float(np.vdot(x, Ay))
     assert abs(a - b) <= 1e-11 * max(abs(a), abs(b), float(np.linalg.norm(x) * np.linalg.norm(Ay)))
     assert float(np.vdot(x, Ax)) > 0.0               # positive definite on the free dofs
+
+
+def test_null_spaces_and_volume_at_full_size(P, ctx):
+    """No boundary conditions, BASELINE grids: K 1 = 0 on every row (natural-face rows included), sum(M 1) = volume,
+    and the elasticity operator annihilates the six rigid-body motions on every row (traction-free faces)."""
+    n, L = [512, 512, 512], [1.0, 0.7, 0.9]
+    nv = 513 ** 3
+    ones = np.ones((1, nv))
+    pk = P._lib.op_params("stiffness", 3, n, L)
+    y = P._lib.op_apply(ctx, pk, ones)
+    assert np.abs(y).max() <= 1e-12 * np.abs(P._lib.op_table(pk)).max()
+    pm = P._lib.op_params("mass", 3, n, L)
+    y = P._lib.op_apply(ctx, pm, ones)
+    assert abs(float(y.sum()) - L[0] * L[1] * L[2]) <= 1e-12
+    assert y.min() > 0.0
+    del y, ones
+    n, L = [640, 128, 128], [1.0, 0.2, 0.2]
+    lam, mu = fo.lame(210e9, 0.3, 3)
+    nn = [k + 1 for k in n]
+    X = [np.linspace(0.0, Lk, k) for Lk, k in zip(L, nn)]
+    x = np.broadcast_to(X[0][None, None, :], nn[::-1])
+    yv = np.broadcast_to(X[1][None, :, None], nn[::-1])
+    z = np.broadcast_to(X[2][:, None, None], nn[::-1])
+    pe = P._lib.op_params("elasticity", 3, n, L, lam=lam, mu=mu)
+    cmax = np.abs(P._lib.op_table(pe)).max()
+    zero = np.zeros(nn[::-1])
+    one = np.ones(nn[::-1])
+    modes = [(one, zero, zero), (zero, one, zero), (zero, zero, one),            # translations
+             (zero, -z, yv), (z, zero, -x), (-yv, x, zero)]                      # rotations about x, y, z
+    for mode in modes:
+        u = np.stack([np.ascontiguousarray(c) for c in mode]).reshape(3, -1)
+        r = P._lib.op_apply(ctx, pe, u)
+        assert np.abs(r).max() <= 1e-12 * cmax * max(1.0, np.abs(u).max())
