@@ -570,3 +570,18 @@ def test_null_spaces_and_volume_at_full_size(P, ctx):
         u = np.stack([np.ascontiguousarray(c) for c in mode]).reshape(3, -1)
         r = P._lib.op_apply(ctx, pe, u)
         assert np.abs(r).max() <= 1e-12 * cmax * max(1.0, np.abs(u).max())
+
+
+@pytest.mark.parametrize("precond", ["gmg", "jacobi"])
+def test_steady_heat_with_end_temperatures_is_exactly_linear(P, precond):
+    """Known answer without the oracle: steady conduction between T_left at x = 0 and T_right at x = Lx with
+    insulated (natural) side faces is linear in x, and a linear field lies in the P1 space, so the nodal values are
+    exact up to the solver tolerance - on a grid far beyond what the CPU restatement can factorise."""
+    Lx, Ly, Lz, n = 2.0, 0.7, 0.5, ([256, 96, 64] if precond == "gmg" else [64, 24, 16])
+    f = P._solve_heat_3d_raw(Lx, Ly, Lz, n[0], n[1], n[2], 1.7, 0.0, 0.0, 0.01, 1, steady=True, T_left=20.0,
+                             T_right=-5.0, precond=precond, as_arrays=True)
+    x = np.asarray(f.coords)[:, 0]
+    exact = 20.0 + (-5.0 - 20.0) * x / Lx
+    u = np.asarray(f.values)[-1]
+    assert np.linalg.norm(u - exact) <= TOL * np.linalg.norm(exact)
+    assert P.last_stats()["converged"] == 1
