@@ -585,3 +585,16 @@ def test_steady_heat_with_end_temperatures_is_exactly_linear(P, precond):
     u = np.asarray(f.values)[-1]
     assert np.linalg.norm(u - exact) <= TOL * np.linalg.norm(exact)
     assert P.last_stats()["converged"] == 1
+
+
+def test_cylinder_branch_without_dirichlet_set_drifts_uniformly(P):
+    """Known answer for the radially weighted path (n4): with T_side only, the BoxMesh 'cylinder' has no Dirichlet
+    facet (reference :594-598 on a box), K_w 1 = 0 and M_w 1 = m_w, so a uniform state with a constant source f
+    advances by exactly dt*f per step on every node."""
+    f = P._solve_heat_3d_raw(1.0, 9.0, 9.0, 48, 60, 60, 0.9, 0.0, 4.0, 0.05, 4, source_type="constant",
+                             source_value=2.5, geometry_type="cylinder", cylinder_radius=0.3, T_side=7.0,
+                             as_arrays=True)
+    v = np.asarray(f.values)
+    assert v.shape == (5, 49 * 37 * 37)
+    for k in range(5):
+        assert np.abs(v[k] - (4.0 + k * 0.05 * 2.5)).max() <= 1e-8 * 4.0
