@@ -598,3 +598,21 @@ def test_cylinder_branch_without_dirichlet_set_drifts_uniformly(P):
     assert v.shape == (5, 49 * 37 * 37)
     for k in range(5):
         assert np.abs(v[k] - (4.0 + k * 0.05 * 2.5)).max() <= 1e-8 * 4.0
+
+
+@pytest.mark.parametrize("nx,precond", [(100, "jacobi"), (4096, "gmg"), (100000, "gmg")])
+def test_heat_1d_sine_mode_decays_by_the_closed_form_factor(P, nx, precond):
+    """(iv-a) on the GPU: sin(j pi x / L) at the nodes is an eigenvector of M = h/6 [1 4 1] and K = 1/h [-1 2 -1]
+    under homogeneous Dirichlet conditions, so every backward-Euler step multiplies it by lam_M / (lam_M + dt k lam_K)."""
+    L, dt, kappa, j, steps = 2.0, 0.01, 1.3, 3, 5
+    h = L / nx
+    x = np.arange(nx + 1) * h
+    u0 = np.sin(j * np.pi * x / L)
+    u0[0] = u0[-1] = 0.0
+    th = j * np.pi * h / L
+    lamM, lamK = h / 6 * (4 + 2 * np.cos(th)), (2 - 2 * np.cos(th)) / h
+    g = lamM / (lamM + dt * kappa * lamK)
+    f = P._solve_heat_1d_raw(L, nx, kappa, 0.0, 0.0, 0.0, dt, steps, u0=u0, precond=precond, as_arrays=True)
+    v = np.asarray(f.values)
+    for k in range(steps + 1):
+        assert np.linalg.norm(v[k] - g ** k * u0) <= TOL * np.linalg.norm(u0), k
