@@ -616,3 +616,18 @@ def test_heat_1d_sine_mode_decays_by_the_closed_form_factor(P, nx, precond):
     v = np.asarray(f.values)
     for k in range(steps + 1):
         assert np.linalg.norm(v[k] - g ** k * u0) <= TOL * np.linalg.norm(u0), k
+
+
+def test_elasticity_scaling_laws(P):
+    """Linearity at a size the oracle cannot reach: the projected von Mises stress is proportional to the body
+    force and independent of E; the von Mises strain is proportional to the force and to 1/E."""
+    args = (1.0, 0.2, 0.2, 160, 32, 32)
+    s1 = np.asarray(P._solve_elasticity_3d_static(*args, 210e9, 0.3, 0.0, 0.0, -76518.0, "stress", as_arrays=True).values[0])
+    s2 = np.asarray(P._solve_elasticity_3d_static(*args, 210e9, 0.3, 0.0, 0.0, -3 * 76518.0, "stress", as_arrays=True).values[0])
+    s3 = np.asarray(P._solve_elasticity_3d_static(*args, 70e9, 0.3, 0.0, 0.0, -76518.0, "stress", as_arrays=True).values[0])
+    e1 = np.asarray(P._solve_elasticity_3d_static(*args, 210e9, 0.3, 0.0, 0.0, -76518.0, "strain", as_arrays=True).values[0])
+    e3 = np.asarray(P._solve_elasticity_3d_static(*args, 70e9, 0.3, 0.0, 0.0, -76518.0, "strain", as_arrays=True).values[0])
+    assert s1.max() > 1e5
+    assert fo.rel_l2(s2, 3.0 * s1) <= 10 * TOL
+    assert fo.rel_l2(s3, s1) <= 10 * TOL
+    assert fo.rel_l2(e3, 3.0 * e1) <= 10 * TOL
