@@ -631,3 +631,17 @@ def test_elasticity_scaling_laws(P):
     assert fo.rel_l2(s2, 3.0 * s1) <= 10 * TOL
     assert fo.rel_l2(s3, s1) <= 10 * TOL
     assert fo.rel_l2(e3, 3.0 * e1) <= 10 * TOL
+
+
+def test_heat_superposition_at_128_cubed(P):
+    """The backward-Euler map is affine in (initial value, boundary value, source): the solve with all three equals
+    the sum of the solves with the initial value alone and with boundary value + source alone (2.1 M dofs, GMG-PCG)."""
+    g = (1.0, 1.0, 1.0, 128, 128, 128, 0.8)
+    a = np.asarray(P._solve_heat_3d_raw(*g, 0.0, 20.0, 0.01, 3, precond="gmg", as_arrays=True).values)
+    b = np.asarray(P._solve_heat_3d_raw(*g, 5.0, 0.0, 0.01, 3, source_type="constant", source_value=3.0, precond="gmg",
+                                        as_arrays=True).values)
+    c = np.asarray(P._solve_heat_3d_raw(*g, 5.0, 20.0, 0.01, 3, source_type="constant", source_value=3.0,
+                                        precond="gmg", as_arrays=True).values)
+    # the boundary nodes of the initial snapshot carry T_boundary in every run: a has 0 there, b has 5, c has 5
+    for k in range(1, 4):
+        assert fo.rel_l2(c[k], a[k] + b[k]) <= 10 * TOL, k
