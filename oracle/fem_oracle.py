@@ -1,6 +1,6 @@
 """CPU oracle: NumPy/SciPy restatement of the FEniCS path of ziyu0425/PDE-Solver.
 
-TEST INFRASTRUCTURE ONLY.  Nothing under ``pde-solver_b200/`` or ``fenics_mcp_server.py``
+TEST INFRASTRUCTURE ONLY.  Nothing under ``pde_solver_b200/`` or ``fenics_mcp_server.py``
 may import this file; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs do, and there only as the checker / CPU baseline.
 

@@ -1,6 +1,6 @@
 """NumPy model of the GPU solver's geometric-multigrid PCG (test infrastructure / tuning aid).
 
-Mirrors pde-solver_b200/csrc/solver.cu: Kuhn edge-midpoint prolongation, R = P^T, rediscretised
+Mirrors pde_solver_b200/csrc/solver.cu: Kuhn edge-midpoint prolongation, R = P^T, rediscretised
 coarse operators, Chebyshev(Jacobi) smoother with the Gershgorin bound, dense coarsest solve."""
 import numpy as np
 import scipy.sparse as sp

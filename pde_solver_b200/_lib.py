@@ -81,7 +81,7 @@ def lib():
             return _lib
         if not os.path.exists(LIB_PATH):
             raise PdeError(
-                f"{LIB_PATH} is missing: build it with `python pde-solver_b200/build.py` "
+                f"{LIB_PATH} is missing: build it with `python pde_solver_b200/build.py` "
                 "(this package has no CPU fallback)")
         L = C.CDLL(LIB_PATH)
         L.pde_last_error.restype = C.c_char_p

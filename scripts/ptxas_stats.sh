@@ -1,6 +1,6 @@
 #!/bin/bash
 # registers / spills per kernel of one source file: scripts/ptxas_stats.sh stencil3d.cu [filter]
-cd "$(dirname "$0")/../pde-solver_b200/csrc" || exit 1
+cd "$(dirname "$0")/../pde_solver_b200/csrc" || exit 1
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr \
   $PDE_B200_NVCC_FLAGS -Xptxas -v -x cu -c "$1" -o /tmp/ptxas_stats.o 2>&1 | python3 -c "
 import sys,re,subprocess

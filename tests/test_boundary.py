@@ -114,7 +114,7 @@ def test_plot_tool_accepts_solver_pickles(server, tmp_path):
 
 def test_product_path_does_not_import_the_oracle():
     # the oracle is test infrastructure: nothing under the package or the server may reference it
-    for base in (os.path.join(ROOT, "pde-solver_b200"), ROOT):
+    for base in (os.path.join(ROOT, "pde_solver_b200"), ROOT):
         for fn in os.listdir(base):
             if fn.endswith(".py") and fn not in ("bench.py", "__graft_entry__.py"):
                 src = open(os.path.join(base, fn)).read()
