@@ -233,6 +233,17 @@ int pde_op_apply(pde_ctx* ctx, const pde_op_params* p, const double* x, double* 
 /* time `reps` device-resident applications (+fused dot); returns mean ms per apply */
 int pde_op_bench(pde_ctx* ctx, const pde_op_params* p, int reps, int warmup, double* ms_per_apply,
                  int64_t* ndofs);
+/* one smoother / residual kernel of the solver on host arrays [ncomp][nverts] (test entry: every mode of the
+ * specialised sweep kernels against the generic kernel and the oracle matrix).
+ *   mode 0: y = A x   1: y = b - A x   2: y = x + c2 D^-1 (b - A x)
+ *   mode 3: y = x + c1 (x - xprev) + c2 D^-1 (b - A x)   4: as 3 with xprev = 0
+ * Dirichlet rows: 0 in modes 0/1, x in modes 2..4.  dots (may be NULL) receives the fused reductions
+ * (modes 0/1: x.y, y.y; modes 2..4: b.y over free rows, second value unspecified). */
+int pde_op_sweep(pde_ctx* ctx, const pde_op_params* p, int32_t mode, double c1, double c2, const double* x,
+                 const double* b, const double* xprev, double* y, double* dots);
+/* as pde_op_bench for one of the sweep modes above (device-resident pattern data) */
+int pde_op_bench_mode(pde_ctx* ctx, const pde_op_params* p, int32_t mode, int32_t reps, int32_t warmup,
+                      double* ms_per_launch, int64_t* ndofs);
 /* solve A x = b (symmetric Dirichlet elimination) from host arrays; PCG per `o` */
 int pde_op_solve(pde_ctx* ctx, const pde_op_params* p, const pde_solver_opts* o, const double* b,
                  double* x, pde_stats* st);

@@ -93,7 +93,7 @@ def lib():
                      "pde_mesh_cells", "pde_dofmap_cells", "pde_boundary_mask", "pde_heat_solve",
                      "pde_heat_open", "pde_heat_set_state", "pde_heat_step", "pde_heat_get_state",
                      "pde_heat_advance_batch", "pde_halo_check",
-                     "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench",
+                     "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench", "pde_op_sweep", "pde_op_bench_mode",
                      "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition", "pde_op_manufactured", "pde_halo_bench", "pde_wheat_solve",
                      "pde_mesh_coords_box"):
             getattr(L, name).restype = C.c_int
@@ -248,6 +248,25 @@ def op_apply(ctx, p, x):
     y = np.empty_like(x)
     check(lib().pde_op_apply(ctx.handle, C.byref(p), ptr(x), ptr(y)))
     return y
+
+
+def op_sweep(ctx, p, mode, x, b=None, xprev=None, c1=0.0, c2=0.0):
+    """One smoother / residual kernel (see pde_op_sweep in include/pde_b200.h); returns (y, dots)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+    xprev = None if xprev is None else np.ascontiguousarray(xprev, dtype=np.float64)
+    y = np.empty_like(x)
+    dots = np.zeros(2)
+    check(lib().pde_op_sweep(ctx.handle, C.byref(p), int(mode), C.c_double(c1), C.c_double(c2), ptr(x),
+                             ptr(b) if b is not None else None, ptr(xprev) if xprev is not None else None, ptr(y),
+                             ptr(dots)))
+    return y, dots
+
+
+def op_bench_mode(ctx, p, mode, reps=20, warmup=3):
+    ms, nd = C.c_double(), C.c_int64()
+    check(lib().pde_op_bench_mode(ctx.handle, C.byref(p), int(mode), int(reps), int(warmup), C.byref(ms), C.byref(nd)))
+    return ms.value, nd.value
 
 
 def op_solve(ctx, p, b, opts=None):

@@ -678,6 +678,91 @@ extern "C" int pde_op_bench(pde_ctx* c, const pde_op_params* p, int reps, int wa
   return 0;
 }
 
+// One smoother / residual kernel of the solver on caller data, so that every mode of the sweep kernels can be checked
+// against the generic table kernel (variant 1) and the oracle matrix.
+//   mode 0: y = A x            1: y = b - A x          2: Chebyshev restart  y = x + c2 D^-1 (b - A x)
+//   mode 3: y = x + c1 (x - xprev) + c2 D^-1 (b - A x), output written over xprev as in the solver
+//   mode 4: as 3 with xprev = 0 (prev_mode 2)
+static int sweep_args(int mode, double c1, double c2, const Field& x, const Field& b, Field& y, StencilArgs* a) {
+  if (mode < 0 || mode > 4) PDE_FAIL("sweep mode must be 0..4");
+  a->x = x.p; a->y = y.p;
+  if (mode >= 1) a->b = b.p;
+  if (mode == 1) { a->bscale = 1.0; a->ascale = -1.0; }
+  if (mode >= 2) { a->cheby = 1; a->c1 = mode == 2 ? 0.0 : c1; a->c2 = c2; }
+  if (mode == 3) { a->prev_mode = 1; a->xprev = y.p; }
+  if (mode == 4) a->prev_mode = 2;
+  return 0;
+}
+
+extern "C" int pde_op_sweep(pde_ctx* c, const pde_op_params* p, int mode, double c1, double c2, const double* x,
+                            const double* b, const double* xprev, double* y, double* dots) {
+  if (!c || !p || !x || !y) PDE_FAIL("null argument");
+  if (mode >= 1 && !b) PDE_FAIL("this sweep mode needs b");
+  if (mode == 3 && !xprev) PDE_FAIL("sweep mode 3 needs xprev");
+  CUDA_OK(cudaSetDevice(c->device));
+  OpGuard G;
+  Field fb;
+  struct Rel { Field* f; ~Rel() { f->release(); } } rel{&fb};
+  int nc;
+  PDE_OK(setup_op(c, p, &G.A, &nc));
+  const Grid& g = G.A.g;
+  PDE_OK(G.x.alloc(c, g, nc));
+  PDE_OK(G.y.alloc(c, g, nc));
+  PDE_OK(fb.alloc(c, g, nc));
+  const long long nloc = (long long)g.nn[0] * g.nn[1] * g.nzl;
+  DevMem dense;
+  PDE_OK(dense.alloc(sizeof(double) * nloc * nc));
+  auto up = [&](const double* h, double* padded) -> int {
+    PDE_OK(h2d(c, dense.p, h, sizeof(double) * nloc * nc));
+    return launch_unpack(c, g, nc, (const double*)dense.p, padded, 0);
+  };
+  PDE_OK(up(x, G.x.p));
+  if (mode >= 1) PDE_OK(up(b, fb.p));
+  if (mode == 3) PDE_OK(up(xprev, G.y.p));
+  StencilArgs a;
+  PDE_OK(sweep_args(mode, c1, c2, G.x, fb, G.y, &a));
+  a.variant = p->variant;
+  a.reduce_slot_xy = S_XY;
+  CUDA_OK(cudaMemsetAsync(c->scal + S_XY, 0, 2 * sizeof(double), c->stream));
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, G.x.p));
+  PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  if (dots) PDE_OK(read_scal(c, S_XY, 2, dots));
+  PDE_OK(launch_pack(c, g, nc, G.y.p, (double*)dense.p, 0));
+  return d2h(c, y, dense.p, sizeof(double) * nloc * nc);
+}
+
+extern "C" int pde_op_bench_mode(pde_ctx* c, const pde_op_params* p, int mode, int reps, int warmup, double* ms_per_launch,
+                                 int64_t* ndofs) {
+  if (!c || !p) PDE_FAIL("null argument");
+  CUDA_OK(cudaSetDevice(c->device));
+  OpGuard G;
+  Field fb;
+  struct Rel { Field* f; ~Rel() { f->release(); } } rel{&fb};
+  int nc;
+  PDE_OK(setup_op(c, p, &G.A, &nc));
+  const Grid& g = G.A.g;
+  PDE_OK(G.x.alloc(c, g, nc));
+  PDE_OK(G.y.alloc(c, g, nc));
+  PDE_OK(fb.alloc(c, g, nc));
+  PDE_OK(launch_fill_pattern(c, g, G.A.bc, nc, G.x.p));
+  PDE_OK(launch_fill_pattern(c, g, G.A.bc, nc, fb.p));
+  StencilArgs a;
+  const double lmax = G.A.dev.gershgorin > 0 ? G.A.dev.gershgorin : 2.0;
+  PDE_OK(sweep_args(mode, 0.1, 1.0 / lmax, G.x, fb, G.y, &a));
+  a.variant = p->variant;
+  a.reduce_slot_xy = S_XY;
+  for (int i = 0; i < warmup; ++i) PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  CUDA_OK(cudaEventRecord(c->ev0, c->stream));
+  for (int i = 0; i < reps; ++i) PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
+  CUDA_OK(cudaEventRecord(c->ev1, c->stream));
+  CUDA_OK(cudaEventSynchronize(c->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  if (ms_per_launch) *ms_per_launch = ms / (reps > 0 ? reps : 1);
+  if (ndofs) *ndofs = (int64_t)g.nn[0] * g.nn[1] * g.nzl * nc;
+  return 0;
+}
+
 static int solve_with(pde_ctx* c, OpGuard& G, const pde_op_params* p, const pde_solver_opts& o, double* x, double* r,
                       double bn2, pde_stats* st) {
   const int nc = G.A.tab.ncomp;

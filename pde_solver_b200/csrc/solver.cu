@@ -315,8 +315,12 @@ int Hierarchy::build(pde_ctx* c, const Operator& fine, int kind, double p0, doub
     }
     if (replicate) {
       PDE_OK(make_grid(dim, n, Lu, 0, 1, &g));
-      PDE_OK(make_grid(dim, n, Lu, c->rank, c->world, &L->gslab));
-      L->gslab.comp_stride = g.comp_stride;   // a window into the replicated array: same pitch, rows and planes
+      // only the FIRST replicated level is restricted into from a slab level and needs this rank's window; the
+      // levels below may have fewer planes than ranks (a cubic 256^3 grid on 4 GPUs coarsens down to nz = 2)
+      if (!lv.back()->replicated) {
+        PDE_OK(make_grid(dim, n, Lu, c->rank, c->world, &L->gslab));
+        L->gslab.comp_stride = g.comp_stride;   // a window into the replicated array: same pitch, rows and planes
+      }
       L->replicated = true;
     } else {
       PDE_OK(make_grid(dim, n, Lu, c->rank, c->world, &g));

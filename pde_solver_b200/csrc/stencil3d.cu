@@ -23,6 +23,7 @@
 #include <type_traits>
 
 #include "device.cuh"
+#include "tma.cuh"
 
 #define SW_STAGES 4
 
@@ -36,35 +37,6 @@ struct SweepGeom {
   int spec;           // 1: the last warp is a dedicated TMA producer (empty/full mbarriers, no CTA barrier)
   int zlo, zhi;       // output plane range [zlo, zhi): [0, nzl), or [-1, nzl+1) when the ghost planes are computed too
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-      : "memory");
-}
 
 template <int NC>
 struct Coef {
@@ -697,7 +669,7 @@ struct TmKey {
 };
 
 // Tensor map of a padded field: (x, y, z incl. the ghost planes, component); out-of-range x/y -> 0.
-static int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by, CUtensorMap* out) {
+int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by, CUtensorMap* out) {
   static std::map<TmKey, CUtensorMap> cache;
   static std::mutex mu;
   TmKey k{(const void*)field, g.nn[0], g.nn[1], g.nzl + 2 * PDE_NG, nc, bx, by, g.PX, g.plane, g.comp_stride};
@@ -719,10 +691,6 @@ static int field_tensor_map(const double* field, const Grid& g, int nc, int bx, 
   return 0;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return (v && *v) ? atoi(v) : dflt;
-}
 
 struct SweepTune {
   int nt, zc, ys, txmax, spec;
@@ -1003,6 +971,8 @@ static int launch_sweep2d_t(pde_ctx* c, const Grid& g, const OpDev& op, const St
   return 0;
 }
 
+int launch_elast3d(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, bool* handled);
+
 int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a,
                         bool* handled) {
   *handled = false;
@@ -1035,6 +1005,12 @@ int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev&
     SWEEP_DISPATCH(1, 4);
   }
   if (op.ncomp == 3) {
+    // the dedicated elasticity kernel (elast3d.cu) takes the launch when the table has the Kuhn-mesh pattern
+    {
+      bool h3 = false;
+      PDE_OK(launch_elast3d(c, g, bc, op, a, &h3));
+      if (h3) return 0;
+    }
     // the vector kernel relies on block(+d) == block(-d) for the in-plane pairs and on zero diagonals of the
     // face-/body-diagonal blocks (both structural for P1 elasticity on the Kuhn split); verify, else generic
     double mx = 0;

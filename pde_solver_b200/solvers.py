@@ -27,6 +27,19 @@ def last_stats():
     return dict(_last_stats)
 
 
+def _record(stats, what, **extra):
+    """Publish the statistics of a finished solve and refuse to hand out an unconverged field: the reference
+    solves with sparse LU (fenics_mcp_server.py:265, 1838), so a PCG that stopped at max_iters is an error here."""
+    _last_stats.clear()
+    _last_stats.update(stats)
+    _last_stats.update(extra)
+    bad = [k for k, d in (("solve", stats), *extra.items()) if isinstance(d, dict) and not d.get("converged", 1)]
+    if bad:
+        d = stats if "solve" in bad else extra[bad[0]]
+        raise _lib.PdeError(f"{what}: PCG did not converge ({', '.join(bad)}; {d.get('iters_total')} iterations, "
+                            f"relative residual {d.get('final_relres'):.3e})")
+
+
 def _embed3(coords, dim):
     out = np.zeros((coords.shape[0], 3), dtype=np.float64)
     out[:, :dim] = coords
@@ -76,8 +89,7 @@ def _heat(dim, L, n, diffusivity, T_initial, dt, num_steps, steady, source_type,
     u0a = np.ascontiguousarray(u0, dtype=np.float64) if u0 is not None else None
     _lib.check(_lib.lib().pde_heat_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(u0a), _lib.ptr(values),
                                          _lib.ptr(times), C.byref(st)))
-    _last_stats.clear()
-    _last_stats.update(st.as_dict())
+    _record(st.as_dict(), "heat solve")
     coords = mesh.coordinates(dim, n, L, ctx)
     return coords, values, times
 
@@ -115,8 +127,7 @@ def _heat_streaming(ctx, p, dim, n, L, rtol, precond, u0, writer):
     finally:
         _lib.lib().pde_heat_close(st_h)
         buf.free()
-    _last_stats.clear()
-    _last_stats.update(acc)
+    _record(acc, "heat solve (streaming)")
     coords = mesh.coordinates(dim, n, L, ctx)
     return coords, np.stack([first, last]), np.array([times[0], times[-1]])
 
@@ -252,8 +263,7 @@ def _heat_3d_special(Lx, Ly, Lz, nx, ny, nz, diffusivity, T_boundary, T_initial,
     o = _lib.make_opts(rtol=rtol, precond="jacobi")
     _lib.check(_lib.lib().pde_wheat_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(values), _lib.ptr(times),
                                           C.byref(st)))
-    _last_stats.clear()
-    _last_stats.update(st.as_dict())
+    _record(st.as_dict(), "heat solve (weighted box)")
     coords = mesh.coordinates_box(3, n, lo, hi, ctx)
     box = geometry_type == "box"
     meta = {"name": "temperature", "unit": "°C", "pde": "heat",
@@ -297,9 +307,7 @@ def _elasticity(dim, L, n, E, nu, body, quantity, plane_stress=True, area=1.0, r
     o = _lib.make_opts(rtol=rtol, precond=precond)
     _lib.check(_lib.lib().pde_elasticity_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(out), _lib.ptr(disp),
                                                C.byref(st), C.byref(sp)))
-    _last_stats.clear()
-    _last_stats.update(st.as_dict())
-    _last_stats["projection"] = sp.as_dict()
+    _record(st.as_dict(), "elasticity solve", projection=sp.as_dict())
     coords = mesh.coordinates(dim, n, L, ctx)
     return coords, out, disp
 
@@ -382,8 +390,7 @@ def _curvilinear(kind, lo, hi, n, bc, diffusivity, T_initial, dt, num_steps, ste
     o = _lib.make_opts(rtol=rtol, precond="jacobi")
     _lib.check(_lib.lib().pde_wheat_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(values), _lib.ptr(times),
                                           C.byref(st)))
-    _last_stats.clear()
-    _last_stats.update(st.as_dict())
+    _record(st.as_dict(), "curvilinear heat solve")
     X = mesh.coordinates_box(dim, n, lo, hi, ctx)
     return X, values, times
 

@@ -101,6 +101,54 @@ def test_operator_apply_matches_oracle(P, ctx, kind, dim, n, variant):
         assert np.abs(y - ref).max() <= 1e-13 * scale * 30
 
 
+@pytest.mark.parametrize("kind,n", [("elasticity", [66, 20, 12]), ("elasticity", [40, 9, 37]), ("elasticity", [200, 9, 36]),
+                                    ("heat", [70, 33, 40]), ("mass", [64, 20, 9])])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_sweep_modes_match_oracle_and_generic_kernel(P, ctx, kind, n, mode):
+    """Every mode of the specialised plane-sweep kernels (apply, residual, Chebyshev restart / with the previous
+    iterate written in place / from a zero previous iterate) against the oracle matrix and the generic table kernel."""
+    dim, L = 3, [1.0, 0.6, 0.35]
+    alpha, beta = (1.0, 0.013) if kind == "heat" else (1.0, 0.0)
+    lam, mu = fo.lame(210e9, 0.3, 3)
+    m, A = _oracle_matrix(kind, dim, n, L, alpha, beta, lam, mu)
+    nc = dim if kind == "elasticity" else 1
+    rng = np.random.default_rng(1)
+    x, b, xp = (rng.standard_normal((nc, m.nv)) for _ in range(3))
+    dinv = 1.0 / A.diagonal().reshape(nc, m.nv)
+    c1, c2 = 0.37, 0.8 / np.abs(A).sum(axis=1).max() * A.diagonal().max()
+    for faces in ({}, {0: 0.0}, {0: 0.0, 3: 0.0, 4: 0.0}, {f: 0.0 for f in range(6)}):
+        on = [f in faces for f in range(6)]
+
+        def pred(xx, ob):
+            sel = np.zeros(xx.shape[0], bool)
+            for ax in range(3):
+                if on[2 * ax]:
+                    sel |= fo.near(xx[:, ax], 0.0)
+                if on[2 * ax + 1]:
+                    sel |= fo.near(xx[:, ax], L[ax])
+            return sel
+        dofs = fo.dirichlet_dofs(m, pred) if faces else np.array([], dtype=int)
+        free = np.ones((nc, m.nv))
+        free[:, dofs] = 0.0
+        Ax = (A @ x.ravel()).reshape(nc, m.nv)
+        if mode == 0:
+            ref = free * Ax
+        elif mode == 1:
+            ref = free * (b - Ax)
+        else:
+            d = {2: 0.0, 3: x - xp, 4: x}[mode]
+            ref = x + free * ((0.0 if mode == 2 else c1) * d + c2 * dinv * (b - Ax))
+        out = {}
+        for variant in (0, 1):
+            p = P._lib.op_params(kind, dim, n, L, alpha, beta, lam, mu, bc=P._lib.make_bc(faces), variant=variant)
+            out[variant], dots = P._lib.op_sweep(ctx, p, mode, x, b, xp, c1, c2)
+            scale = np.abs(A).max() * np.abs(x).max() * (1.0 if mode < 2 else c2 * dinv.max())
+            assert np.abs(out[variant] - ref).max() <= 3e-12 * max(scale, 1.0), (faces, variant)
+            want = (x * ref).sum() if mode < 2 else (free * b * ref).sum()
+            assert abs(dots[0] - want) <= 1e-9 * (np.abs(x * ref).sum() + np.abs(b * ref).sum()), (faces, variant)
+        assert np.abs(out[0] - out[1]).max() <= 3e-12 * max(scale, 1.0)
+
+
 # ---------------------------------------------------------------- heat solves vs oracle LU
 def _check_heat(P, dim, L, n, okw, gkw, precond):
     ref = fo.solve_heat(dim, L, n, **okw)
