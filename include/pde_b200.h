@@ -101,7 +101,8 @@ typedef struct pde_solver_opts {
   int32_t cheby_degree; /* GMG smoother sweeps per side (default 2) */
   int32_t check_every;  /* host convergence poll interval in iterations */
   double cheby_ratio;   /* smoothing interval [lmax/ratio, lmax] */
-  int32_t reserved[4];
+  int32_t verify_residual; /* 0: recompute ||b - A x||/||b|| after the last solve of a call (pde_stats.true_relres); -1: off */
+  int32_t reserved[3];
 } pde_solver_opts;
 void pde_solver_opts_default(pde_solver_opts* o);
 

@@ -20,7 +20,7 @@ class Bc(C.Structure):
 class SolverOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("max_iters", C.c_int32), ("precond", C.c_int32),
                 ("cheby_degree", C.c_int32), ("check_every", C.c_int32), ("cheby_ratio", C.c_double),
-                ("reserved", C.c_int32 * 4)]
+                ("verify_residual", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class Stats(C.Structure):
@@ -130,7 +130,8 @@ def make_bc(faces=None, side_excludes_xends=False):
     return bc
 
 
-def make_opts(rtol=1e-10, precond="auto", max_iters=100000, cheby_degree=2, check_every=10, cheby_ratio=8.0):
+def make_opts(rtol=1e-10, precond="auto", max_iters=100000, cheby_degree=2, check_every=10, cheby_ratio=8.0,
+              verify=True):
     o = SolverOpts()
     lib().pde_solver_opts_default(C.byref(o))
     o.rtol = float(rtol)
@@ -139,6 +140,7 @@ def make_opts(rtol=1e-10, precond="auto", max_iters=100000, cheby_degree=2, chec
     o.cheby_degree = int(cheby_degree)
     o.check_every = int(check_every)
     o.cheby_ratio = float(cheby_ratio)
+    o.verify_residual = 0 if verify else -1     # recompute ||b - A x||/||b|| after the last solve of a call
     return o
 
 

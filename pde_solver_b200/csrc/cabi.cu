@@ -258,6 +258,7 @@ struct pde_heat_state {
   PcgWork w;
   Field u, r;
   Field uold, e;          // previous step and increment: x0 = u_n + (u_n - u_{n-1})
+  Field un;               // u_n of a verified solve (true-residual check), allocated on first use
   bool extrap = false;
   DevMem dense;
   long long nloc = 0;
@@ -339,7 +340,7 @@ extern "C" int pde_heat_close(pde_heat_state* s) {
   s->A.release(); s->K.release(); s->M.release();
   s->mg.release();
   s->w.release();
-  s->u.release(); s->r.release(); s->uold.release(); s->e.release();
+  s->u.release(); s->r.release(); s->uold.release(); s->e.release(); s->un.release();
   delete s;
   return 0;
 }
@@ -432,10 +433,16 @@ extern "C" int pde_heat_get_state(pde_heat_state* s, double* u_host) {
   return d2h(c, u_host, s->dense.p, sizeof(double) * s->nloc);
 }
 
-static int heat_one_solve(pde_heat_state* s, pde_stats* st) {
+// verify: also recompute the true residual ||b - A u_{n+1}|| / ||b|| of this solve (st->true_relres) instead of
+// trusting the PCG recurrence (SURVEY hard part 3).  Costs one copy of u_n and two operator applications.
+static int heat_one_solve(pde_heat_state* s, pde_stats* st, bool verify = false) {
   pde_ctx* c = s->c;
   const pde_heat_params& p = s->p;
   const double f = p.source_value, kappa = p.diffusivity;
+  if (verify && !p.steady) {
+    if (!s->un.p) PDE_OK(s->un.alloc(c, s->g, 1));
+    PDE_OK(launch_copy(c, s->g, 1, s->un.p, s->u.p));
+  }
   StencilArgs a;
   a.x = s->u.p; a.y = s->r.p; a.bconst[0] = f; a.reduce_slot_xy = S_XY;
   if (c->world > 1) PDE_OK(comm_halo_exchange(c, s->g, 1, s->u.p));
@@ -469,7 +476,28 @@ static int heat_one_solve(pde_heat_state* s, pde_stats* st) {
       }
     }
   }
-  return pcg_solve(c, s->A, s->use_mg ? &s->mg : nullptr, s->w, s->u.p, s->r.p, bn2, s->o, st);
+  PDE_OK(pcg_solve(c, s->A, s->use_mg ? &s->mg : nullptr, s->w, s->u.p, s->r.p, bn2, s->o, st));
+  if (verify) {
+    StencilArgs t;
+    t.y = s->r.p; t.reduce_slot_xy = S_XY;
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, s->g, 1, s->u.p));
+    if (p.steady) {   // residual of the reduced system: f m - kappa K u on the free rows
+      t.x = s->u.p; t.bconst[0] = f; t.bscale = 1.0; t.ascale = -1.0;
+      PDE_OK(launch_stencil(c, s->g, s->bc, s->A.dev, t));
+    } else {          // b = M u_n + dt f m, then b - A u_{n+1}
+      if (c->world > 1) PDE_OK(comm_halo_exchange(c, s->g, 1, s->un.p));
+      StencilArgs tb;
+      tb.x = s->un.p; tb.y = s->r.p; tb.bconst[0] = f; tb.bscale = p.dt; tb.ascale = 1.0;
+      PDE_OK(launch_stencil(c, s->g, s->bc, s->M.dev, tb));
+      t.x = s->u.p; t.b = s->r.p; t.bscale = 1.0; t.ascale = -1.0;
+      PDE_OK(launch_stencil(c, s->g, s->bc, s->A.dev, t));
+    }
+    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
+    double rr;
+    PDE_OK(read_scal(c, S_YY, 1, &rr));
+    st->true_relres = bn2 > 0 ? std::sqrt(rr / bn2) : 0.0;
+  }
+  return 0;
 }
 
 static void stats_init(pde_stats* st, long long ndofs) {
@@ -488,7 +516,7 @@ extern "C" int pde_heat_step(pde_heat_state* s, int nsteps, pde_stats* st_out) {
   const long long l0 = c->launches;
   CUDA_OK(cudaEventRecord(c->ev0, c->stream));
   for (int k = 0; k < nsteps; ++k) {
-    PDE_OK(heat_one_solve(s, &st));
+    PDE_OK(heat_one_solve(s, &st, k == nsteps - 1 && s->o.verify_residual >= 0));
     s->steps_done += 1;
   }
   CUDA_OK(cudaEventRecord(c->ev1, c->stream));
@@ -960,6 +988,16 @@ extern "C" int pde_elasticity_solve(pde_ctx* c, const pde_elast_params* p, const
   CUDA_OK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
   st.solve_ms = ms - st.setup_ms;
   st.launches = c->launches - l0;
+  if (o.verify_residual >= 0) {
+    // true residual b - A u of the returned displacement (kappa ~ 5e8 at config 5: do not trust the recurrence)
+    StencilArgs t = a;
+    if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, G.x.p));
+    PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, t));
+    if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 2));
+    double rr;
+    PDE_OK(read_scal(c, S_YY, 1, &rr));
+    st.true_relres = bn2 > 0 ? std::sqrt(rr / bn2) : 0.0;
+  }
   // projected scalar: M v = sum_cells value_c |c|/(d+1)   (project(eq_expr, Vs), :1541-1546, 1714, 1862)
   SimplexGeom sg;
   build_simplex_geom(dim, g.h, &sg);

@@ -179,6 +179,7 @@ struct StencilArgs {
   int reduce_slot_xy = -1;        // scal slot receiving sum x.y (and +1: sum y.y) ; -1: none
   int ghost_out = 0;              // slabs: also compute the ghost planes z = -1 and z = nzl of y (uniform-diagonal
                                   // operators on the sweep kernel only; needs 2 halo planes of x, 1 of b; no reductions)
+  int skip_yy = 0;                // the y.y reduction is not needed (PCG only uses x.y = p.Ap)
   int variant = 0;
 };
 

@@ -29,21 +29,33 @@
 
 namespace {
 
-constexpr int E_TX = 32, E_NS = 4, E_YS = 2;
-constexpr int E_TY = E_NS * E_YS;                  // 8 rows per tile
-constexpr int E_BX = E_TX + 4, E_BY = E_TY + 2;    // input box: origin (x0-2, y0-1) (the TMA start must be 16-byte aligned)
-constexpr int E_XCOMP = E_BX * E_BY;               // doubles per component of an input box
-constexpr int E_XBOX = 3 * E_XCOMP;                // 8640 bytes arrive per input box
-constexpr int E_XSTAGE = (E_XBOX + 15) / 16 * 16;  // padded: every TMA destination stays 128-byte aligned
-constexpr int E_TCOMP = E_TX * E_TY;
-constexpr int E_TILE = 3 * E_TCOMP;                // 6144 bytes: one plane of the output tile, three components
-constexpr int E_STAGES = 4;
-constexpr int E_NT = E_TX * E_NS;
-static_assert((E_XSTAGE * 8) % 128 == 0 && (E_TILE * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned");
-
-#ifndef E_MINB
-#define E_MINB 4
+// tile width / strips per tile / pipeline depth: compile-time so that every shared-memory access is base + immediate
+// (A/B builds: PDE_B200_NVCC_FLAGS="-DE_TX_=64 -DE_NS_=4")
+#ifndef E_TX_
+#define E_TX_ 32
 #endif
+#ifndef E_NS_
+#define E_NS_ 4
+#endif
+#ifndef E_STAGES_
+#define E_STAGES_ 4
+#endif
+constexpr int E_TX = E_TX_, E_NS = E_NS_;          // a warp owns (part of) one strip of YS rows across the tile
+constexpr int E_BX = E_TX + 4;                     // input box: origin (x0-2, y0-1) (the TMA start must be 16-byte aligned)
+constexpr int E_STAGES = E_STAGES_;
+static_assert(E_TX % 32 == 0, "strips must not share a warp");
+constexpr int E_NT = E_TX * E_NS;
+template <int YS>
+struct EG {
+  static constexpr int TY = E_NS * YS;             // rows per tile
+  static constexpr int BY = TY + 2;
+  static constexpr int XCOMP = E_BX * BY;          // doubles per component of an input box
+  static constexpr int XBOX = 3 * XCOMP;           // doubles that arrive per input box
+  static constexpr int XSTAGE = (XBOX + 15) / 16 * 16;   // padded: every TMA destination stays 128-byte aligned
+  static constexpr int TCOMP = E_TX * TY;
+  static constexpr int TILE = 3 * TCOMP;           // one plane of the output tile, three components
+  static_assert((TILE * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned");
+};
 
 enum { EM_APPLY = 0, EM_RESID = 1, EM_CHEBY = 2 };
 
@@ -52,15 +64,18 @@ struct ECoef {
   double uxy, uxz, uyz, uxy2;          // coupling units; uxy2 = 2 uxy
 };
 struct EArgs {
+  double* y;
   double bB[3];    // apply: bscale * bconst[c] * load
   double c2d[3];   // Chebyshev: c2 / diag[c]
   double ascale, bscale, c1;
-  int prev_mode, do_reduce, has_y;
+  int prev_mode, do_reduce, has_y, need_yy;
 };
 struct EGeom {
   int nn0, nn1, nzl, z0, nzg;
   int ntx, nty, nzc, zc;
   int on[6], side_excl;
+  int PX;
+  long long plane, comp_stride;
 };
 
 // Contribution of input component B of the resident plane to the outputs one plane below (aP: this plane is their
@@ -68,10 +83,9 @@ struct EGeom {
 //   V[r][c]: plane values at strip rows r-1 (r = 0..YS+1), columns c-1 (c = 0..2); V[0][2] and V[YS+1][0] are unused.
 // Coupling patterns in units u_ab (offsets 0, +-x, +-y, +-z, +-(x+y), +-(x+z), +-(y+z), +-(x+y+z)):
 //   xy: -4  2  2 -1 -2  1  1 -1      xz: -4  2 -1  2  1 -2  1 -1      yz: -4 -1  2  2  1  1 -2 -1
-template <int B>
-__device__ __forceinline__ void e_contrib(const ECoef& C, const double (&V)[E_YS + 2][3], double (&aP)[E_YS][3],
-                                          double (&a0)[E_YS][3], double (&aM)[E_YS][3]) {
-  constexpr int YS = E_YS;
+template <int B, int YS>
+__device__ __forceinline__ void e_contrib(const ECoef& C, const double (&V)[YS + 2][3], double (&aP)[YS][3],
+                                          double (&a0)[YS][3], double (&aM)[YS][3]) {
   double P[YS + 2], Q[YS + 2];
   if (B != 1) {
 #pragma unroll
@@ -135,28 +149,30 @@ __device__ __forceinline__ void e_contrib(const ECoef& C, const double (&V)[E_YS
 //       EM_RESID  y = m (ascale A x + bscale b)       reductions x.y, y.y
 //       EM_CHEBY  y = x + m (c1 d + c2 D^-1 (b - A x)) reduction b.y ; d = x - x_prev (PREV: x_prev is loaded),
 //                 x (prev_mode 2: the previous iterate is zero) or 0 (restart)
-template <int MODE, bool PREV>
-__global__ void __launch_bounds__(E_NT, E_MINB)
+// TOUT: the output plane is staged in shared memory and written by a TMA store (which clips at the domain boundary);
+//       otherwise every thread stores its own values (no shared-memory traffic, but address arithmetic and predicates).
+template <int MODE, bool PREV, int YS, bool TOUT>
+__global__ void __launch_bounds__(E_NT, (YS <= 2 ? 512 : 384) / E_NT)
 k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
           const __grid_constant__ CUtensorMap tmp, const __grid_constant__ CUtensorMap tmy,
           const __grid_constant__ ECoef C, const __grid_constant__ EArgs a, const __grid_constant__ EGeom ge,
           ReduceBuf red, double* red_out) {
-  constexpr int YS = E_YS;
+  using G = EG<YS>;
   constexpr bool HAS_B = MODE != EM_APPLY;
   constexpr bool CHEBY = MODE == EM_CHEBY;
   constexpr int NAUX = (HAS_B ? 1 : 0) + (PREV ? 1 : 0);
-  constexpr int STAGE_ELEMS = E_XSTAGE + NAUX * E_TILE;
+  constexpr int STAGE_ELEMS = G::XSTAGE + NAUX * G::TILE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* const stage0 = reinterpret_cast<double*>(smem_raw);
   double* const ybuf0 = stage0 + E_STAGES * STAGE_ELEMS;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(ybuf0 + 2 * E_TILE);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(ybuf0 + (TOUT ? 2 * G::TILE : 0));
 
   const int t = threadIdx.x;
   const int item = blockIdx.x;
   const int itx = item % ge.ntx;
   const int ity = (item / ge.ntx) % ge.nty;
   const int izc = item / (ge.ntx * ge.nty);
-  const int x0 = itx * E_TX, y0 = ity * E_TY;
+  const int x0 = itx * E_TX, y0 = ity * G::TY;
   const int za = izc * ge.zc;
   const int zb = min(za + ge.zc, ge.nzl);
   const int nplanes = zb - za + 2;   // input planes za-1 .. zb
@@ -167,14 +183,14 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
 
   // step n: input plane za-1+n, and (n >= 2) the right-hand side / previous iterate of output plane za+n-2
   auto issue = [&](int n) {
-    const uint32_t bar = bar0 + 8 * (n & (E_STAGES - 1));
-    const uint32_t dst = stg0 + (n & (E_STAGES - 1)) * STAGE_BYTES;
+    const uint32_t bar = bar0 + 8 * (n % E_STAGES);
+    const uint32_t dst = stg0 + (n % E_STAGES) * STAGE_BYTES;
     const bool aux = NAUX > 0 && n >= 2;
-    mbar_expect_tx(bar, (uint32_t)(E_XBOX * 8 + (aux ? NAUX * E_TILE * 8 : 0)));
+    mbar_expect_tx(bar, (uint32_t)(G::XBOX * 8 + (aux ? NAUX * G::TILE * 8 : 0)));
     tma_load_4d(dst, &tmx, x0 - 2, y0 - 1, za - 1 + n + PDE_NG, 0, bar);
     if (aux) {
-      if (HAS_B) tma_load_4d(dst + E_XSTAGE * 8, &tmb, x0, y0, za + n - 2 + PDE_NG, 0, bar);
-      if (PREV) tma_load_4d(dst + (E_XSTAGE + E_TILE) * 8, &tmp, x0, y0, za + n - 2 + PDE_NG, 0, bar);
+      if (HAS_B) tma_load_4d(dst + G::XSTAGE * 8, &tmb, x0, y0, za + n - 2 + PDE_NG, 0, bar);
+      if (PREV) tma_load_4d(dst + (G::XSTAGE + G::TILE) * 8, &tmp, x0, y0, za + n - 2 + PDE_NG, 0, bar);
     }
   };
   if (t == 0) {
@@ -186,15 +202,16 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
   if (t == 0)
     for (int n = 0; n < E_STAGES - 1 && n < nplanes; ++n) issue(n);
 
-  const int lx = t & (E_TX - 1);
-  const int st = t >> 5;
+  const int lx = t % E_TX;
+  const int st = t / E_TX;
   const int ix = x0 + lx;
-  const int xoff = (st * YS) * E_BX + lx + 1;   // V[r][c] of component q: stage[q*E_XCOMP + xoff + r*E_BX + c]
-  const int toff = (st * YS) * E_TX + lx;       // tile element (q, row j): [q*E_TCOMP + toff + j*E_TX]
+  const int iy0 = y0 + st * YS;
+  const int xoff = (st * YS) * E_BX + lx + 1;   // V[r][c] of component q: stage[q*XCOMP + xoff + r*E_BX + c]
+  const int toff = (st * YS) * E_TX + lx;       // tile element (q, row j): [q*TCOMP + toff + j*E_TX]
 
-  // row flags, constant over the march.  free: not Dirichlet through an x/y face; slow: free but on a natural x/y
-  // face (k_face_rows computes it).  mgen = rows this kernel computes on a generic plane.
-  double mgen[YS], kgen[YS], fre[YS];
+  // row flags (bit j = row j of the strip), constant over the march.  fre: inside the domain and not Dirichlet through
+  // an x/y face; slow: free but on a natural x/y face (k_face_rows computes it); okb: inside the domain.
+  unsigned fre = 0, slow = 0, okb = 0;
   bool z_excl = false;   // "other_faces" rule of the reference: the z faces skip the x-end columns
   {
     const bool xin = ix < ge.nn0;
@@ -202,17 +219,18 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
     z_excl = ge.side_excl && (xe0 || xe1);
 #pragma unroll
     for (int j = 0; j < YS; ++j) {
-      const int iy = y0 + st * YS + j;
+      const int iy = iy0 + j;
       const bool ye0 = iy == 0, ye1 = iy == ge.nn1 - 1;
       bool d = (xe0 && ge.on[0]) || (xe1 && ge.on[1]);
       if (!d && !z_excl) d = (ye0 && ge.on[2]) || (ye1 && ge.on[3]);
-      const bool f = xin && iy < ge.nn1 && !d;
-      const bool slow = f && (xe0 || xe1 || ye0 || ye1);
-      fre[j] = f ? 1.0 : 0.0;
-      kgen[j] = slow ? 1.0 : 0.0;
-      mgen[j] = (f && !slow) ? 1.0 : 0.0;
+      const bool in = xin && iy < ge.nn1;
+      if (in) okb |= 1u << j;
+      if (in && !d) fre |= 1u << j;
+      if (in && !d && (xe0 || xe1 || ye0 || ye1)) slow |= 1u << j;
     }
   }
+  const unsigned fast = fre & ~slow;            // rows this kernel computes on a generic plane
+  double* yrun = a.y + ((long long)ge.PX * iy0 + ix) + ge.plane * za;   // direct stores: column pointer at plane za
 
   double accA[YS][3], accB[YS][3], accC[YS][3];
 #pragma unroll
@@ -224,8 +242,8 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
   // One pipeline step: input plane za-1+i is resident in stage i % STAGES; output plane za+i-2 retires (FIN).
   auto body = [&](auto fin_tag, int i, double (&aP)[YS][3], double (&a0)[YS][3], double (&aM)[YS][3]) {
     constexpr bool FIN = decltype(fin_tag)::value;
-    const int stage = i & (E_STAGES - 1);
-    mbar_wait(bar0 + 8 * stage, (uint32_t)((i >> 2) & 1));
+    const int stage = i % E_STAGES;
+    mbar_wait(bar0 + 8 * stage, (uint32_t)((i / E_STAGES) & 1));
     const double* const sx = stage0 + stage * STAGE_ELEMS;
     {
       const double* const sp = sx + xoff;
@@ -236,10 +254,22 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
         for (int r = 0; r < YS + 2; ++r)
 #pragma unroll
           for (int c = 0; c < 3; ++c)
-            V[r][c] = ((r == 0 && c == 2) || (r == YS + 1 && c == 0)) ? 0.0 : sp[q * E_XCOMP + r * E_BX + c];
-        if (q == 0) e_contrib<0>(C, V, aP, a0, aM);
-        if (q == 1) e_contrib<1>(C, V, aP, a0, aM);
-        if (q == 2) e_contrib<2>(C, V, aP, a0, aM);
+            V[r][c] = ((r == 0 && c == 2) || (r == YS + 1 && c == 0)) ? 0.0 : sp[q * G::XCOMP + r * E_BX + c];
+#ifdef E_NOMATH   // memory-only probe build: same transfers and shared-memory reads, (almost) no arithmetic
+#pragma unroll
+        for (int j = 0; j < YS; ++j) {
+          double s = 0.0;
+#pragma unroll
+          for (int r = 0; r < YS + 2; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s += V[r][c];
+          aP[j][q] += s; aM[j][q] = s; a0[j][q] += C.k0[q] * s;
+        }
+#else
+        if (q == 0) e_contrib<0, YS>(C, V, aP, a0, aM);
+        if (q == 1) e_contrib<1, YS>(C, V, aP, a0, aM);
+        if (q == 2) e_contrib<2, YS>(C, V, aP, a0, aM);
+#endif
       }
     }
     const int zout = za + i - 2;
@@ -249,47 +279,54 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
       const bool zface = gz == 0 || gz == ge.nzg - 1;
       const bool zface_dir = (gz == 0 && ge.on[4]) || (gz == ge.nzg - 1 && ge.on[5]);
       const bool zdir = gz < 0 || gz > ge.nzg - 1 || (zface_dir && !z_excl);
-      const double mz = (zdir || zface) ? 0.0 : 1.0;
-      const double kz = (!zdir && zface) ? 1.0 : 0.0;
+      const unsigned comp = (zdir || zface) ? 0u : fast;             // rows computed here
+      const unsigned keep = zdir ? 0u : (zface ? fre : slow);        // rows left to k_face_rows
       // own-column values of the retiring plane: still resident in the stage of the step before
-      const double* const xo_s = stage0 + ((i - 1) & (E_STAGES - 1)) * STAGE_ELEMS + xoff + E_BX + 1;
-      const double* const bt = sx + E_XSTAGE + toff;
-      const double* const pt = bt + E_TILE;
-      double* const yt = ybuf0 + (i & 1) * E_TILE + toff;
+      const double* const xo_s = stage0 + ((i - 1) % E_STAGES) * STAGE_ELEMS + xoff + E_BX + 1;
+      const double* const bt = sx + G::XSTAGE + toff;
+      const double* const pt = bt + G::TILE;
+      double* const yt = ybuf0 + (i & 1) * G::TILE + toff;
+      const unsigned stmask = a.has_y ? (okb & ~keep) : 0u;          // direct stores: rows written by this kernel
 #pragma unroll
       for (int j = 0; j < YS; ++j) {
-        const double m = mgen[j] * mz;
-        const double k = fma(kgen[j], mz, fre[j] * kz);   // rows left to k_face_rows
+        const bool m = (comp >> j) & 1u;
+        const bool k = (keep >> j) & 1u;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-          const double xo = xo_s[q * E_XCOMP + j * E_BX];
+          const double xo = xo_s[q * G::XCOMP + j * E_BX];
           const double A = aP[j][q];
           double yv;
           if (CHEBY) {
-            const double Bv = bt[q * E_TCOMP + j * E_TX];
+            const double Bv = bt[q * G::TCOMP + j * E_TX];
             double dprev;
-            if (PREV) dprev = xo - pt[q * E_TCOMP + j * E_TX];
+            if (PREV) dprev = xo - pt[q * G::TCOMP + j * E_TX];
             else dprev = a.prev_mode == 2 ? xo : 0.0;
-            const double dn = m * fma(a.c1, dprev, a.c2d[q] * (Bv - A));
-            // PREV: the output may alias x_prev, which k_face_rows still reads on its rows: hand it back there
-            yv = PREV ? xo + fma(-k, dprev, dn) : xo + dn;
-            red_xy = fma(m * Bv, yv, red_xy);
+            const double dn = m ? fma(a.c1, dprev, a.c2d[q] * (Bv - A)) : 0.0;
+            yv = xo + dn;
+            // TMA output, PREV: the output may alias x_prev, which k_face_rows still reads on its rows: hand it back
+            if (TOUT && PREV) yv = k ? xo - dprev : yv;
+            red_xy = fma(m ? Bv : 0.0, yv, red_xy);
           } else {
-            const double Bt = HAS_B ? a.bscale * bt[q * E_TCOMP + j * E_TX] : a.bB[q];
-            yv = m * fma(a.ascale, A, Bt);
+            const double Bt = HAS_B ? a.bscale * bt[q * G::TCOMP + j * E_TX] : a.bB[q];
+            yv = m ? fma(a.ascale, A, Bt) : 0.0;
             red_xy = fma(xo, yv, red_xy);
-            red_yy = fma(yv, yv, red_yy);
+            if (a.need_yy) red_yy = fma(yv, yv, red_yy);
           }
-          yt[q * E_TCOMP + j * E_TX] = yv;
+          if (TOUT) yt[q * G::TCOMP + j * E_TX] = yv;
+          else if ((stmask >> j) & 1u) yrun[q * ge.comp_stride + j * (long long)ge.PX] = yv;
         }
       }
-      if (t == 0) tma_store_wait_read0();   // the store of the step before has released the other output buffer
-      fence_proxy_async();
+      if (TOUT) {
+        if (t == 0) tma_store_wait_read0();   // the store of the step before has released the other output buffer
+        fence_proxy_async();
+      } else {
+        yrun += ge.plane;
+      }
     }
     __syncthreads();   // stage (i-1) and the tiles of stage i are consumed; the output tile is complete
     if (t == 0) {
-      if (FIN && a.has_y) {
-        tma_store_4d(&tmy, yb0 + (i & 1) * (E_TILE * 8), x0, y0, zout + PDE_NG, 0);
+      if (TOUT && FIN && a.has_y) {
+        tma_store_4d(&tmy, yb0 + (i & 1) * (G::TILE * 8), x0, y0, zout + PDE_NG, 0);
         tma_store_commit();
       }
       if (i + E_STAGES - 1 < nplanes) issue(i + E_STAGES - 1);
@@ -305,7 +342,7 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
     if (i + 1 < nplanes) body(T_{}, i + 1, accA, accB, accC);
     if (i + 2 < nplanes) body(T_{}, i + 2, accB, accC, accA);
   }
-  if (t == 0) tma_store_wait_all();
+  if (TOUT && t == 0) tma_store_wait_all();
 
   if (a.do_reduce) {
     if (CHEBY) {
@@ -349,25 +386,35 @@ bool extract_coef(const OpDev& op, ECoef* C) {
   return true;
 }
 
-template <int MODE, bool PREV>
+struct ETune {
+  int ys, tout, zc;
+};
+const ETune& etune() {
+  static ETune t = {env_int("PDE_B200_E_YS", 2), env_int("PDE_B200_E_TOUT", 1), env_int("PDE_B200_E_ZC", 64)};
+  return t;
+}
+
+template <int MODE, bool PREV, int YS, bool TOUT>
 int launch_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, const ECoef& C) {
+  using G = EG<YS>;
   constexpr int NAUX = (MODE != EM_APPLY ? 1 : 0) + (PREV ? 1 : 0);
   EGeom ge;
   ge.nn0 = g.nn[0]; ge.nn1 = g.nn[1]; ge.nzl = g.nzl; ge.z0 = g.z0; ge.nzg = g.nzg;
   for (int i = 0; i < 6; ++i) ge.on[i] = bc.on[i];
   ge.side_excl = bc.side_excl;
+  ge.PX = g.PX; ge.plane = g.plane; ge.comp_stride = g.comp_stride;
   ge.ntx = (g.nn[0] + E_TX - 1) / E_TX;
-  ge.nty = (g.nn[1] + E_TY - 1) / E_TY;
-  static const int zc_env = env_int("PDE_B200_E_ZC", 64);
-  int zc = zc_env < 2 ? 2 : zc_env;
+  ge.nty = (g.nn[1] + G::TY - 1) / G::TY;
+  int zc = etune().zc < 2 ? 2 : etune().zc;
   while (zc > 4 && (long long)ge.ntx * ge.nty * ((g.nzl + zc - 1) / zc) < 8LL * c->sm_count) zc /= 2;
   ge.nzc = (g.nzl + zc - 1) / zc;
   ge.zc = (g.nzl + ge.nzc - 1) / ge.nzc;
   ge.nzc = (g.nzl + ge.zc - 1) / ge.zc;
   const long long items = (long long)ge.ntx * ge.nty * ge.nzc;
   if (items > RED_MAX_BLOCKS) PDE_FAIL("elasticity sweep grid exceeds the reduction buffer");
-  const size_t smem = ((size_t)E_STAGES * (E_XSTAGE + NAUX * E_TILE) + 2 * E_TILE) * sizeof(double) + E_STAGES * sizeof(uint64_t);
-  auto kern = k_elast3d<MODE, PREV>;
+  const size_t smem = ((size_t)E_STAGES * (G::XSTAGE + NAUX * G::TILE) + (TOUT ? 2 * G::TILE : 0)) * sizeof(double) +
+                      E_STAGES * sizeof(uint64_t);
+  auto kern = k_elast3d<MODE, PREV, YS, TOUT>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -375,12 +422,13 @@ int launch_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const 
     attr_set = true;
   }
   CUtensorMap tmx, tmb, tmp, tmy;
-  PDE_OK(field_tensor_map(a.x, g, 3, E_BX, E_BY, &tmx));
+  PDE_OK(field_tensor_map(a.x, g, 3, E_BX, G::BY, &tmx));
   tmb = tmp = tmy = tmx;   // unused maps still have to be valid kernel parameters
-  if (MODE != EM_APPLY) PDE_OK(field_tensor_map(a.b, g, 3, E_TX, E_TY, &tmb));
-  if (PREV) PDE_OK(field_tensor_map(a.xprev, g, 3, E_TX, E_TY, &tmp));
-  if (a.y) PDE_OK(field_tensor_map(a.y, g, 3, E_TX, E_TY, &tmy));
+  if (MODE != EM_APPLY) PDE_OK(field_tensor_map(a.b, g, 3, E_TX, G::TY, &tmb));
+  if (PREV) PDE_OK(field_tensor_map(a.xprev, g, 3, E_TX, G::TY, &tmp));
+  if (TOUT && a.y) PDE_OK(field_tensor_map(a.y, g, 3, E_TX, G::TY, &tmy));
   EArgs ea;
+  ea.y = a.y;
   for (int i = 0; i < 3; ++i) {
     ea.bB[i] = a.bscale * a.bconst[i] * op.h_load_int;
     ea.c2d[i] = a.c2 * op.h_dinv_int[i];
@@ -389,12 +437,21 @@ int launch_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const 
   ea.prev_mode = a.prev_mode;
   ea.do_reduce = a.reduce_slot_xy >= 0;
   ea.has_y = a.y != nullptr;
+  ea.need_yy = ea.do_reduce && !a.skip_yy;
   double* out = ea.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
   kern<<<(unsigned)items, E_NT, smem, c->stream>>>(tmx, tmb, tmp, tmy, C, ea, ge, c->red, out);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   if (!op.uniform_diag) PDE_OK(launch_face_rows(c, g, bc, op, a));
   return 0;
+}
+
+template <int YS, bool TOUT>
+int launch_mode(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, const ECoef& C) {
+  if (a.cheby)
+    return a.prev_mode == 1 ? launch_t<EM_CHEBY, true, YS, TOUT>(c, g, bc, op, a, C)
+                            : launch_t<EM_CHEBY, false, YS, TOUT>(c, g, bc, op, a, C);
+  return a.b ? launch_t<EM_RESID, false, YS, TOUT>(c, g, bc, op, a, C) : launch_t<EM_APPLY, false, YS, TOUT>(c, g, bc, op, a, C);
 }
 
 }  // namespace
@@ -410,6 +467,15 @@ int launch_elast3d(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, 
   ECoef C;
   if (!extract_coef(op, &C)) return 0;
   *handled = true;
-  if (a.cheby) return a.prev_mode == 1 ? launch_t<EM_CHEBY, true>(c, g, bc, op, a, C) : launch_t<EM_CHEBY, false>(c, g, bc, op, a, C);
-  return a.b ? launch_t<EM_RESID, false>(c, g, bc, op, a, C) : launch_t<EM_APPLY, false>(c, g, bc, op, a, C);
+  const int ys = etune().ys;
+  const bool tout = etune().tout != 0;
+#define E_DISPATCH(YS_)                                                \
+  do {                                                                 \
+    if (tout) return launch_mode<YS_, true>(c, g, bc, op, a, C);       \
+    return launch_mode<YS_, false>(c, g, bc, op, a, C);                \
+  } while (0)
+  if (ys == 3) E_DISPATCH(3);
+  if (ys == 4) E_DISPATCH(4);
+  E_DISPATCH(2);
+#undef E_DISPATCH
 }

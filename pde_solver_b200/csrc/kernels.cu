@@ -270,61 +270,103 @@ struct FaceSet {
   long long start[7];             // prefix sums of the node counts
 };
 
-template <int NC, bool CHEBY>
-__global__ void __launch_bounds__(128)
+// FULL: the 3-D stencil with all 15 offsets in table order.  The kernel is bound by its coefficient reads, not by the
+// field data (15 x NC x NC table loads per node against 15 x NC field loads; 141 us per launch on the cantilever faces
+// of 1280x256x256 against 0.75 ms for the whole interior sweep when they are __ldg'ed per node): a block first marks
+// the node classes it meets, copies those rows of the class table into shared memory, and every node then reads its
+// coefficients as warp-uniform shared-memory broadcasts.  The 15 x NC field loads of a node are issued together.
+#define FACE_NT 256
+template <int NC, bool CHEBY, bool FULL>
+__global__ void __launch_bounds__(FACE_NT)
 k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, const __grid_constant__ FaceSet fs,
             const double* __restrict__ coef, const double* __restrict__ dinv, const double* __restrict__ load,
             const __grid_constant__ StencilDev a, ReduceBuf red, double* red_out) {
+  constexpr int ROW = PDE_NOFF * NC * NC;
+  __shared__ double s_coef[FULL ? PDE_NCLASS * ROW : 1];
+  __shared__ int s_flag[PDE_NCLASS];
   double acc_xy = 0.0, acc_yy = 0.0;
   const long long total = fs.start[fs.nface];
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    int f = 0;
-    while (f + 1 < fs.nface && t >= fs.start[f + 1]) ++f;
-    const long long r = t - fs.start[f];
-    const int u = fs.lo[f][0] + (int)(r % fs.cnt[f][0]);
-    const int v = fs.lo[f][1] + (int)(r / fs.cnt[f][0]);
-    int ix, iy, lz;
-    if (fs.axis[f] == 0) { ix = fs.fixed[f]; iy = u; lz = v; }
-    else if (fs.axis[f] == 1) { ix = u; iy = fs.fixed[f]; lz = v; }
-    else { ix = u; iy = v; lz = fs.fixed[f]; }
-    const int gz = lz + g.z0;
-    double bcv;
-    if (bc_node(g, bc, ix, iy, gz, &bcv)) continue;  // Dirichlet rows were written (masked) by the main kernel
-    const int cls = node_class(g, ix, iy, gz);
-    const long long idx = (long long)g.PX * iy + g.plane * lz + ix;
-    double acc[NC];
-#pragma unroll
-    for (int i = 0; i < NC; ++i) acc[i] = 0.0;
-    for (int k = 0; k < g.nk; ++k) {
-      const double* cf = coef + ((size_t)cls * PDE_NOFF + g.kidx[k]) * (NC * NC);
-      const long long off = g.koff[k];
-      double xv[NC];
-#pragma unroll
-      for (int j = 0; j < NC; ++j) xv[j] = a.x[idx + off + j * g.comp_stride];
-#pragma unroll
-      for (int i = 0; i < NC; ++i)
-#pragma unroll
-        for (int j = 0; j < NC; ++j) acc[i] = fma(__ldg(cf + i * NC + j), xv[j], acc[i]);
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+    const long long t = base + threadIdx.x;
+    bool live = t < total;
+    int ix = 0, iy = 0, lz = 0, cls = 13;
+    if (live) {
+      int f = 0;
+      while (f + 1 < fs.nface && t >= fs.start[f + 1]) ++f;
+      const long long r = t - fs.start[f];
+      const int u = fs.lo[f][0] + (int)(r % fs.cnt[f][0]);
+      const int v = fs.lo[f][1] + (int)(r / fs.cnt[f][0]);
+      if (fs.axis[f] == 0) { ix = fs.fixed[f]; iy = u; lz = v; }
+      else if (fs.axis[f] == 1) { ix = u; iy = fs.fixed[f]; lz = v; }
+      else { ix = u; iy = v; lz = fs.fixed[f]; }
+      double bcv;
+      if (bc_node(g, bc, ix, iy, lz + g.z0, &bcv)) live = false;  // Dirichlet rows were written (masked) by the main kernel
+      cls = node_class(g, ix, iy, lz + g.z0);
     }
-    const double ld = a.b ? 0.0 : __ldg(load + cls);
+    if (FULL) {
+      if (threadIdx.x < PDE_NCLASS) s_flag[threadIdx.x] = 0;
+      __syncthreads();
+      if (live) s_flag[cls] = 1;
+      __syncthreads();
+      for (int k = 0; k < PDE_NCLASS; ++k)
+        if (s_flag[k])
+          for (int e = threadIdx.x; e < ROW; e += blockDim.x) s_coef[k * ROW + e] = __ldg(coef + (size_t)k * ROW + e);
+      __syncthreads();
+    }
+    if (live) {
+      const long long idx = (long long)g.PX * iy + g.plane * lz + ix;
+      double acc[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      const long long ii = idx + i * g.comp_stride;
-      const double B = a.b ? a.b[ii] : a.bconst[i] * ld;
-      if (CHEBY) {
-        const double xo = a.x[ii];
-        const double dprev = a.prev_mode == 1 ? xo - a.xprev[ii] : (a.prev_mode == 2 ? xo : 0.0);
-        const double dn = a.c1 * dprev + a.c2 * __ldg(dinv + cls * NC + i) * (B - acc[i]);
-        const double yv = xo + dn;
-        a.y[ii] = yv;
-        acc_xy = fma(B, yv, acc_xy);
+      for (int i = 0; i < NC; ++i) acc[i] = 0.0;
+      if (FULL) {
+        double xv[PDE_NOFF][NC];
+#pragma unroll
+        for (int k = 0; k < PDE_NOFF; ++k) {
+          const long long off = kOffDdev(k, g.PX, g.plane);
+#pragma unroll
+          for (int j = 0; j < NC; ++j) xv[k][j] = a.x[idx + off + j * g.comp_stride];
+        }
+        const double* cf = s_coef + cls * ROW;
+#pragma unroll
+        for (int k = 0; k < PDE_NOFF; ++k)
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[i] = fma(cf[k * NC * NC + i * NC + j], xv[k][j], acc[i]);
       } else {
-        const double yv = a.bscale * B + a.ascale * acc[i];
-        if (a.y) a.y[ii] = yv;
-        acc_xy = fma(a.x[ii], yv, acc_xy);
-        acc_yy = fma(yv, yv, acc_yy);
+        for (int k = 0; k < g.nk; ++k) {
+          const double* cf = coef + ((size_t)cls * PDE_NOFF + g.kidx[k]) * (NC * NC);
+          const long long off = g.koff[k];
+          double xv[NC];
+#pragma unroll
+          for (int j = 0; j < NC; ++j) xv[j] = a.x[idx + off + j * g.comp_stride];
+#pragma unroll
+          for (int i = 0; i < NC; ++i)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) acc[i] = fma(__ldg(cf + i * NC + j), xv[j], acc[i]);
+        }
+      }
+      const double ld = a.b ? 0.0 : __ldg(load + cls);
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const long long ii = idx + i * g.comp_stride;
+        const double B = a.b ? a.b[ii] : a.bconst[i] * ld;
+        if (CHEBY) {
+          const double xo = a.x[ii];
+          const double dprev = a.prev_mode == 1 ? xo - a.xprev[ii] : (a.prev_mode == 2 ? xo : 0.0);
+          const double dn = a.c1 * dprev + a.c2 * __ldg(dinv + cls * NC + i) * (B - acc[i]);
+          const double yv = xo + dn;
+          a.y[ii] = yv;
+          acc_xy = fma(B, yv, acc_xy);
+        } else {
+          const double yv = a.bscale * B + a.ascale * acc[i];
+          if (a.y) a.y[ii] = yv;
+          acc_xy = fma(a.x[ii], yv, acc_xy);
+          acc_yy = fma(yv, yv, acc_yy);
+        }
       }
     }
+    if (FULL) __syncthreads();   // the flags and the table rows are rebuilt by the next trip
   }
   if (a.do_reduce) {
     if (CHEBY) {
@@ -373,15 +415,22 @@ int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op
   sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2; sd.s0 = a.s0;
   sd.do_reduce = a.reduce_slot_xy >= 0;
   sd.first2 = 0;
-  int blocks = flat_blocks(c, total, 128);
+  // one node per thread while the grid fits the reduction buffer: the kernel is latency-bound, not bandwidth-bound
+  long long nb = (total + FACE_NT - 1) / FACE_NT;
+  if (nb > RED_MAX_BLOCKS) nb = RED_MAX_BLOCKS;
+  const int blocks = (int)nb;
+  bool full = g.dim == 3 && g.nk == PDE_NOFF;
+  for (int k = 0; full && k < PDE_NOFF; ++k) full = g.kidx[k] == k;
   double* out = sd.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
+#define FACE_LAUNCH(CH, FU)                                                                                      \
+  DISPATCH_NC(op.ncomp, (k_face_rows<NC, CH, FU><<<blocks, FACE_NT, 0, c->stream>>>(g, bc, fs, op.coef, op.dinv, op.load, \
+                                                                               sd, c->red, out)))
   if (a.cheby) {
-    DISPATCH_NC(op.ncomp, (k_face_rows<NC, true><<<blocks, 128, 0, c->stream>>>(g, bc, fs, op.coef, op.dinv, op.load, sd,
-                                                                               c->red, out)));
+    if (full) { FACE_LAUNCH(true, true); } else { FACE_LAUNCH(true, false); }
   } else {
-    DISPATCH_NC(op.ncomp, (k_face_rows<NC, false><<<blocks, 128, 0, c->stream>>>(g, bc, fs, op.coef, op.dinv, op.load,
-                                                                                sd, c->red, out)));
+    if (full) { FACE_LAUNCH(false, true); } else { FACE_LAUNCH(false, false); }
   }
+#undef FACE_LAUNCH
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -662,6 +662,7 @@ int pcg_solve(pde_ctx* c, const Operator& A, Hierarchy* mg, PcgWork& w, double* 
     const int sr = 2 * (it & 1), sn = 2 * (1 - (it & 1));
     StencilArgs a;
     a.x = w.p.p; a.y = w.q.p; a.reduce_slot_xy = S_XY;
+    a.skip_yy = 1;   // only p.Ap is needed
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, w.p.p));
     PDE_OK(launch_stencil(c, g, A.bc, A.dev, a));
     if (c->world > 1) PDE_OK(comm_allreduce_scal(c, S_XY, 1));

@@ -142,11 +142,11 @@ def test_sweep_modes_match_oracle_and_generic_kernel(P, ctx, kind, n, mode):
         for variant in (0, 1):
             p = P._lib.op_params(kind, dim, n, L, alpha, beta, lam, mu, bc=P._lib.make_bc(faces), variant=variant)
             out[variant], dots = P._lib.op_sweep(ctx, p, mode, x, b, xp, c1, c2)
-            scale = np.abs(A).max() * np.abs(x).max() * (1.0 if mode < 2 else c2 * dinv.max())
-            assert np.abs(out[variant] - ref).max() <= 3e-12 * max(scale, 1.0), (faces, variant)
+            scale = max(np.abs(A).max() * np.abs(x).max(), np.abs(ref).max())
+            assert np.abs(out[variant] - ref).max() <= 3e-12 * scale, (faces, variant)
             want = (x * ref).sum() if mode < 2 else (free * b * ref).sum()
             assert abs(dots[0] - want) <= 1e-9 * (np.abs(x * ref).sum() + np.abs(b * ref).sum()), (faces, variant)
-        assert np.abs(out[0] - out[1]).max() <= 3e-12 * max(scale, 1.0)
+        assert np.abs(out[0] - out[1]).max() <= 3e-12 * scale
 
 
 # ---------------------------------------------------------------- heat solves vs oracle LU
@@ -161,6 +161,7 @@ def _check_heat(P, dim, L, n, okw, gkw, precond):
         assert fo.rel_l2(f.values[k], ref.values[k]) <= TOL, (k, fo.rel_l2(f.values[k], ref.values[k]))
     st = P.last_stats()
     assert st["converged"] == 1
+    assert st["true_relres"] <= 1e-9, st      # recomputed b - A u of the last step, not the PCG recurrence
     return f, st
 
 
@@ -284,6 +285,7 @@ def test_elasticity_3d(P, precond, quantity):
     err = fo.rel_l2(f.values[0], ref.values[0])
     assert err <= TOL, err
     assert P.last_stats()["converged"] == 1
+    assert P.last_stats()["true_relres"] <= 1e-9, P.last_stats()
 
 
 @pytest.mark.parametrize("precond", ["jacobi", "gmg"])
