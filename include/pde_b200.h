@@ -58,6 +58,9 @@ int pde_slab_partition(int dim, const int32_t n[3], int rank, int world, int lev
  * dim-D mesh; returns mean ms per exchange and the bytes this rank sends per exchange */
 int pde_halo_bench(pde_ctx* ctx, int dim, const int32_t n[3], int ncomp, int reps, double* ms_per_exchange,
                    int64_t* bytes_sent);
+/* what the multi-GPU layer does on this context: halo_path 0 = no exchange yet / single GPU, 1 = NCCL send/recv,
+ * 2 = peer-memory mailbox kernel over NVLink; counts of halo exchanges and all-reduces issued so far */
+int pde_comm_info(pde_ctx* ctx, int32_t* halo_path, int64_t* halo_exchanges, int64_t* allreduces);
 /* self-check of the halo exchange (peer-memory kernel or NCCL): `reps` exchanges of `depth` planes of a field
  * defined by the global node index; *mismatches = ghost entries that differ bitwise from the owner's values */
 int pde_halo_check(pde_ctx* ctx, int dim, const int32_t n[3], int ncomp, int depth, int reps, int64_t* mismatches);

@@ -93,7 +93,7 @@ def lib():
                      "pde_mesh_cells", "pde_dofmap_cells", "pde_boundary_mask", "pde_heat_solve",
                      "pde_heat_open", "pde_heat_set_state", "pde_heat_step", "pde_heat_get_state",
                      "pde_heat_advance_batch", "pde_halo_check",
-                     "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench", "pde_op_sweep", "pde_op_bench_mode",
+                     "pde_heat_close", "pde_elasticity_solve", "pde_op_table", "pde_op_apply", "pde_op_bench", "pde_op_sweep", "pde_op_bench_mode", "pde_comm_info",
                      "pde_op_solve", "pde_version", "pde_host_alloc", "pde_host_free", "pde_slab_partition", "pde_op_manufactured", "pde_halo_bench", "pde_wheat_solve",
                      "pde_mesh_coords_box"):
             getattr(L, name).restype = C.c_int
@@ -278,6 +278,14 @@ def op_solve(ctx, p, b, opts=None):
     o = opts if opts is not None else make_opts()
     check(lib().pde_op_solve(ctx.handle, C.byref(p), C.byref(o), ptr(b), ptr(x), C.byref(st)))
     return x, st.as_dict()
+
+
+def comm_info(ctx):
+    """{"halo_path": none / nccl send-recv / peer-memory kernel, "halo_exchanges": n, "allreduces": n} so far."""
+    hp, ne, na = C.c_int32(), C.c_int64(), C.c_int64()
+    check(lib().pde_comm_info(ctx.handle, C.byref(hp), C.byref(ne), C.byref(na)))
+    return {"halo_path": {0: "none", 1: "nccl send/recv", 2: "peer-memory mailbox kernel (cudaIpc over NVLink)"}[hp.value],
+            "halo_exchanges": ne.value, "allreduces": na.value}
 
 
 def halo_check(ctx, dim, n, ncomp=1, depth=1, reps=4):

@@ -28,6 +28,7 @@ extern "C" int pde_ctx_create(int device, pde_ctx** out) {
   CUDA_OK(cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming));
   CUDA_OK(cudaMalloc(&c->red.partials, sizeof(double) * RED_MAX_BLOCKS * RED_MAX_VALS));
   CUDA_OK(cudaMalloc(&c->red.counter, sizeof(unsigned)));
+  CUDA_OK(cudaMalloc(&c->face_partials, sizeof(double) * RED_MAX_BLOCKS * RED_MAX_VALS));
   CUDA_OK(cudaMemsetAsync(c->red.counter, 0, sizeof(unsigned), c->stream));
   CUDA_OK(cudaMalloc(&c->scal, sizeof(double) * S_NSLOTS));
   CUDA_OK(cudaMemsetAsync(c->scal, 0, sizeof(double) * S_NSLOTS, c->stream));
@@ -44,6 +45,7 @@ extern "C" int pde_ctx_destroy(pde_ctx* c) {
   comm_destroy(c);
   cudaFree(c->red.partials);
   cudaFree(c->red.counter);
+  cudaFree(c->face_partials);
   cudaFree(c->scal);
   cudaFreeHost(c->h_scal);
   cudaEventDestroy(c->ev0);

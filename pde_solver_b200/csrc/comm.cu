@@ -318,8 +318,20 @@ int comm_destroy(pde_ctx* c) {
   return 0;
 }
 
+// what the multi-GPU layer actually does (bench.py reports it instead of assuming): halo path 0 = none yet / single
+// GPU, 1 = NCCL send/recv, 2 = peer-memory mailbox kernel; exchanges and all-reduces issued so far
+extern "C" int pde_comm_info(pde_ctx* c, int32_t* halo_path, int64_t* halo_exchanges, int64_t* allreduces) {
+  if (!c) PDE_FAIL("null context");
+  P2pHalo* h = (P2pHalo*)c->p2p;
+  if (halo_path) *halo_path = c->world == 1 ? 0 : (h && h->ok ? 2 : (h && h->tried ? 1 : 0));
+  if (halo_exchanges) *halo_exchanges = c->n_halo;
+  if (allreduces) *allreduces = c->n_allreduce;
+  return 0;
+}
+
 int comm_allreduce_scal(pde_ctx* c, int slot, int count) {
   if (c->world == 1) return 0;
+  c->n_allreduce++;
   NCCL_OK(c->nccl->AllReduce(c->scal + slot, c->scal + slot, (size_t)count, /*ncclFloat64*/ 8, /*ncclSum*/ 0,
                              c->nccl_comm, c->stream));
   return 0;
@@ -327,6 +339,7 @@ int comm_allreduce_scal(pde_ctx* c, int slot, int count) {
 
 int comm_allreduce_buf(pde_ctx* c, double* buf, size_t count) {
   if (c->world == 1 || count == 0) return 0;
+  c->n_allreduce++;
   NCCL_OK(c->nccl->AllReduce(buf, buf, count, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream));
   return 0;
 }
@@ -336,6 +349,7 @@ int comm_halo_exchange(pde_ctx* c, const Grid& g, int ncomp, double* f, int dept
   if (depth < 1 || depth > PDE_NG) PDE_FAIL("halo depth out of range");
   if (depth > g.nzl) PDE_FAIL("halo deeper than the slab");
   const size_t n = (size_t)g.plane * depth;   // `depth` consecutive planes are contiguous
+  c->n_halo++;
   PDE_OK(p2p_ensure(c, n * ncomp * sizeof(double)));
   P2pHalo* h = (P2pHalo*)c->p2p;
   if (h && h->ok) {

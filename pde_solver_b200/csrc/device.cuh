@@ -21,6 +21,7 @@ struct pde_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
   ReduceBuf red{};
+  double* face_partials = nullptr;   // [RED_MAX_BLOCKS][RED_MAX_VALS]: block sums of a deferred face-row kernel
   double* scal = nullptr;     // device [S_NSLOTS]
   double* h_scal = nullptr;   // pinned, mapped host mirror [S_NSLOTS]
   double* h_scal_dev = nullptr;  // device-side address of h_scal
@@ -30,6 +31,7 @@ struct pde_ctx {
   void* nccl_comm = nullptr;
   NcclApi* nccl = nullptr;
   void* p2p = nullptr;        // peer-memory halo mailboxes (comm.cu), null until the first exchange
+  long long n_halo = 0, n_allreduce = 0;   // exchanges / all-reduces issued so far (pde_comm_info)
 };
 
 // ---- geometry helpers -----------------------------------------------------------------
@@ -70,8 +72,11 @@ __device__ __forceinline__ long long kOffDdev(int k, int PX, long long plane) {
 // deterministic two-stage reduction: per-block partials, last block sums them in fixed order
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+// extra / nextra: partial sums [nextra][RED_MAX_VALS] left by an EARLIER kernel (the deferred face-row kernel), added
+// by the last block in fixed order
 template <int NV, bool ACC = false>
-__device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], ReduceBuf red, double* out) {
+__device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], ReduceBuf red, double* out,
+                                                      const double* extra = nullptr, int nextra = 0) {
   __shared__ double sm[NV][32];
   __shared__ bool is_last;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -106,6 +111,7 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], ReduceBuf
   for (int i = 0; i < NV; ++i) {
     double s = 0.0;
     for (unsigned b = tid; b < gridDim.x; b += nth) s += red.partials[(size_t)b * RED_MAX_VALS + i];
+    for (int b = tid; b < nextra; b += nth) s += extra[(size_t)b * RED_MAX_VALS + i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
     __syncthreads();
@@ -189,7 +195,10 @@ bool sweep_applicable(const Grid& g, int ncomp);
 int launch_post2(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const double* x0, const double* b,
                  double* y, double c2_0, double c1_1, double c2_1, int dot_slot, bool* handled);
 // rows of the non-Dirichlet nodes on the domain faces (class-table stencil); reductions are ADDED to the slot
-int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
+// defer_blocks != nullptr: the kernel only leaves its block sums in c->face_partials (*defer_blocks of them); the
+// sweep kernel launched AFTER it adds them in its own finalize (no fence / atomic ticket per face block)
+int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a,
+                     int* defer_blocks = nullptr);
 // Jacobi-PCG fused update: x += a p, r -= a q, rho_new = r.dinv r, rr = r.r  (a = rho/pAp from scal)
 int launch_cg_update(pde_ctx* c, const Grid& g, const OpDev& op, double* x, double* r, const double* p,
                      const double* q, int slot_rho, int slot_pap, int slot_rho_new, int slot_rr, int jacobi);

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(E_NT, (YS <= 2 ? 512 : 384) / E_NT)
 k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
           const __grid_constant__ CUtensorMap tmp, const __grid_constant__ CUtensorMap tmy,
           const __grid_constant__ ECoef C, const __grid_constant__ EArgs a, const __grid_constant__ EGeom ge,
-          ReduceBuf red, double* red_out) {
+          ReduceBuf red, double* red_out, const double* face_part, int nface_part) {
   using G = EG<YS>;
   constexpr bool HAS_B = MODE != EM_APPLY;
   constexpr bool CHEBY = MODE == EM_CHEBY;
@@ -347,10 +347,10 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
   if (a.do_reduce) {
     if (CHEBY) {
       double v[1] = {red_xy};
-      block_reduce_finalize<1>(v, red, red_out);
+      block_reduce_finalize<1>(v, red, red_out, face_part, nface_part);
     } else {
       double v[2] = {red_xy, red_yy};
-      block_reduce_finalize<2>(v, red, red_out);
+      block_reduce_finalize<2>(v, red, red_out, face_part, nface_part);
     }
   }
 }
@@ -390,7 +390,7 @@ struct ETune {
   int ys, tout, zc;
 };
 const ETune& etune() {
-  static ETune t = {env_int("PDE_B200_E_YS", 2), env_int("PDE_B200_E_TOUT", 1), env_int("PDE_B200_E_ZC", 64)};
+  static ETune t = {env_int("PDE_B200_E_YS", 2), env_int("PDE_B200_E_TOUT", 0), env_int("PDE_B200_E_ZC", 64)};
   return t;
 }
 
@@ -439,10 +439,15 @@ int launch_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const 
   ea.has_y = a.y != nullptr;
   ea.need_yy = ea.do_reduce && !a.skip_yy;
   double* out = ea.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
-  kern<<<(unsigned)items, E_NT, smem, c->stream>>>(tmx, tmb, tmp, tmy, C, ea, ge, c->red, out);
+  // Natural faces.  Direct stores never touch the rows of k_face_rows, so that kernel can run FIRST and leave its
+  // block sums for this kernel's finalize (no fence + atomic ticket in each of its ~5000 latency-bound blocks).  With
+  // the TMA output path this kernel writes whole tiles, so the face rows have to be written after it.
+  int nfp = 0;
+  if (!TOUT && !op.uniform_diag) PDE_OK(launch_face_rows(c, g, bc, op, a, &nfp));
+  kern<<<(unsigned)items, E_NT, smem, c->stream>>>(tmx, tmb, tmp, tmy, C, ea, ge, c->red, out, c->face_partials, nfp);
   c->launches++;
   CUDA_OK(cudaGetLastError());
-  if (!op.uniform_diag) PDE_OK(launch_face_rows(c, g, bc, op, a));
+  if (TOUT && !op.uniform_diag) PDE_OK(launch_face_rows(c, g, bc, op, a));
   return 0;
 }
 

@@ -30,6 +30,7 @@ struct StencilDev {
   double bscale, ascale, c1, c2, s0;
   int do_reduce;
   int first2;
+  double* defer;   // face rows: leave the block sums here instead of finalizing
 };
 
 template <int NC, bool CHEBY>
@@ -161,6 +162,7 @@ static int launch_stencil_t(pde_ctx* c, const Grid& g, const BcDev& bc, const Op
   for (int i = 0; i < 3; ++i) sd.bconst[i] = a.bconst[i];
   sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2; sd.s0 = a.s0;
   sd.first2 = a.cheby == 2;
+  sd.defer = nullptr;
   sd.do_reduce = a.reduce_slot_xy >= 0;
   RowLaunch rl = row_launch(c, g);
   double* out = sd.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
@@ -267,108 +269,157 @@ struct FaceSet {
   int nface;
   int axis[6], fixed[6];          // fixed axis and its index (z: LOCAL plane)
   int lo[6][2], cnt[6][2];        // the two varying axes (ascending axis order): start and count
-  long long start[7];             // prefix sums of the node counts
+  int tiles0[6];                  // tiles of FACE_TU nodes along the first varying axis
+  int tstart[7];                  // prefix sums of the tile counts: one CTA per FACE_TU x FACE_TV tile
 };
+#define FACE_TU 32
+#define FACE_TV 8
+#define FACE_NT (FACE_TU * FACE_TV)
 
-// FULL: the 3-D stencil with all 15 offsets in table order.  The kernel is bound by its coefficient reads, not by the
-// field data (15 x NC x NC table loads per node against 15 x NC field loads; 141 us per launch on the cantilever faces
-// of 1280x256x256 against 0.75 ms for the whole interior sweep when they are __ldg'ed per node): a block first marks
-// the node classes it meets, copies those rows of the class table into shared memory, and every node then reads its
-// coefficients as warp-uniform shared-memory broadcasts.  The 15 x NC field loads of a node are issued together.
-#define FACE_NT 256
+// One CTA per 32 x 8 tile of a face (warp = 32 consecutive nodes along the first varying axis, the 8 warps are 8
+// consecutive lines along the second): the three lines / planes a node needs are shared with the warps next to it, so
+// most of the 15 x NC loads hit L1.  FULL: the 3-D stencil with all 15 offsets in table order.  The kernel is latency
+// bound (a few wide dependent steps, little data), so everything a node reads from HBM - its 15 x NC neighbours, its
+// own x / b / x_prev - is requested FIRST; while those loads fly the block marks the node classes it meets and copies
+// those rows of the class table into shared memory (a face tile meets one to three of the 27), and the products then
+// read the coefficients as warp-uniform shared-memory broadcasts.
+// History on the cantilever faces of 1280x256x256 (1.38 M nodes): 141 us with per-node __ldg'ed coefficients and a
+// rolled offset loop, against 0.75 ms for the whole interior sweep.
 template <int NC, bool CHEBY, bool FULL>
-__global__ void __launch_bounds__(FACE_NT)
+__global__ void __launch_bounds__(FACE_NT, FULL ? 2 : 1)
 k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, const __grid_constant__ FaceSet fs,
             const double* __restrict__ coef, const double* __restrict__ dinv, const double* __restrict__ load,
             const __grid_constant__ StencilDev a, ReduceBuf red, double* red_out) {
   constexpr int ROW = PDE_NOFF * NC * NC;
-  __shared__ double s_coef[FULL ? PDE_NCLASS * ROW : 1];
-  __shared__ int s_flag[PDE_NCLASS];
+  constexpr int ROWP = (ROW + 1) / 2 * 2;   // rows stay 16-byte aligned
+  __shared__ __align__(16) double s_coef[FULL ? PDE_NCLASS * ROWP : 2];
+  __shared__ unsigned s_mask, s_nz[PDE_NCLASS];
   double acc_xy = 0.0, acc_yy = 0.0;
-  const long long total = fs.start[fs.nface];
-  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
-    const long long t = base + threadIdx.x;
-    bool live = t < total;
-    int ix = 0, iy = 0, lz = 0, cls = 13;
+  {
+    const int tile = blockIdx.x;
+    int f = 0;
+#pragma unroll
+    for (int q = 1; q < 6; ++q) f += (q < fs.nface && tile >= fs.tstart[q]) ? 1 : 0;
+    const int tl = tile - fs.tstart[f];
+    const int tv = tl / fs.tiles0[f], tu = tl - tv * fs.tiles0[f];
+    const int ul = tu * FACE_TU + (threadIdx.x & (FACE_TU - 1)), vl = tv * FACE_TV + (threadIdx.x / FACE_TU);
+    bool live = ul < fs.cnt[f][0] && vl < fs.cnt[f][1];
+    const int u = fs.lo[f][0] + ul, v = fs.lo[f][1] + vl;
+    int ix, iy, lz;
+    if (fs.axis[f] == 0) { ix = fs.fixed[f]; iy = u; lz = v; }
+    else if (fs.axis[f] == 1) { ix = u; iy = fs.fixed[f]; lz = v; }
+    else { ix = u; iy = v; lz = fs.fixed[f]; }
+    int cls = 13;
     if (live) {
-      int f = 0;
-      while (f + 1 < fs.nface && t >= fs.start[f + 1]) ++f;
-      const long long r = t - fs.start[f];
-      const int u = fs.lo[f][0] + (int)(r % fs.cnt[f][0]);
-      const int v = fs.lo[f][1] + (int)(r / fs.cnt[f][0]);
-      if (fs.axis[f] == 0) { ix = fs.fixed[f]; iy = u; lz = v; }
-      else if (fs.axis[f] == 1) { ix = u; iy = fs.fixed[f]; lz = v; }
-      else { ix = u; iy = v; lz = fs.fixed[f]; }
       double bcv;
       if (bc_node(g, bc, ix, iy, lz + g.z0, &bcv)) live = false;  // Dirichlet rows were written (masked) by the main kernel
       cls = node_class(g, ix, iy, lz + g.z0);
     }
+    // 32-bit element offsets from three component bases (the host checks that a component triple fits 2^31 elements):
+    // one add + one widening multiply-add per load instead of a 64-bit address rebuild
+    const long long idxl = live ? (long long)g.PX * iy + g.plane * lz + ix : 0;   // dead lanes read around node 0 (in bounds)
+    const int idx = (int)idxl;   // FULL only
+    const double* xc[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) xc[j] = a.x + j * g.comp_stride;
+    double xv[PDE_NOFF][NC], xo[NC], bv[NC], pv[NC];
     if (FULL) {
-      if (threadIdx.x < PDE_NCLASS) s_flag[threadIdx.x] = 0;
+#pragma unroll
+      for (int k = 0; k < PDE_NOFF; ++k) {
+        const int off = (int)kOffDdev(k, g.PX, g.plane);
+#pragma unroll
+        for (int j = 0; j < NC; ++j) xv[k][j] = xc[j][idx + off];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      xo[i] = xc[i][idxl];
+      bv[i] = a.b ? (a.b + i * g.comp_stride)[idxl] : 0.0;
+      pv[i] = (CHEBY && a.prev_mode == 1) ? (a.xprev + i * g.comp_stride)[idxl] : 0.0;
+    }
+    if (FULL) {
+      if (threadIdx.x < PDE_NCLASS) s_nz[threadIdx.x] = 0u;
+      if (threadIdx.x == 0) s_mask = 0u;
       __syncthreads();
-      if (live) s_flag[cls] = 1;
+      const unsigned mine = __reduce_or_sync(0xffffffffu, live ? (1u << cls) : 0u);
+      if ((threadIdx.x & 31) == 0 && mine) atomicOr(&s_mask, mine);
       __syncthreads();
-      for (int k = 0; k < PDE_NCLASS; ++k)
-        if (s_flag[k])
-          for (int e = threadIdx.x; e < ROW; e += blockDim.x) s_coef[k * ROW + e] = __ldg(coef + (size_t)k * ROW + e);
+      for (unsigned m = s_mask; m; m &= m - 1) {
+        const int k = __ffs(m) - 1;
+        for (int e = threadIdx.x; e < ROW; e += blockDim.x) {
+          const double cv = __ldg(coef + (size_t)k * ROW + e);
+          s_coef[k * ROWP + e] = cv;
+          if (cv != 0.0) atomicOr(&s_nz[k], 1u << (e / (NC * NC)));   // offsets whose block is not identically zero
+        }
+      }
       __syncthreads();
     }
     if (live) {
-      const long long idx = (long long)g.PX * iy + g.plane * lz + ix;
       double acc[NC];
 #pragma unroll
       for (int i = 0; i < NC; ++i) acc[i] = 0.0;
       if (FULL) {
-        double xv[PDE_NOFF][NC];
+        const double* cf = s_coef + cls * ROWP;
+        const unsigned nz = s_nz[cls];
+        // a face node has no neighbours beyond the face: a third of its blocks are zero (warp-uniform skip)
 #pragma unroll
         for (int k = 0; k < PDE_NOFF; ++k) {
-          const long long off = kOffDdev(k, g.PX, g.plane);
-#pragma unroll
-          for (int j = 0; j < NC; ++j) xv[k][j] = a.x[idx + off + j * g.comp_stride];
-        }
-        const double* cf = s_coef + cls * ROW;
-#pragma unroll
-        for (int k = 0; k < PDE_NOFF; ++k)
+          if (!((nz >> k) & 1u)) continue;
 #pragma unroll
           for (int i = 0; i < NC; ++i)
 #pragma unroll
             for (int j = 0; j < NC; ++j) acc[i] = fma(cf[k * NC * NC + i * NC + j], xv[k][j], acc[i]);
+        }
       } else {
         for (int k = 0; k < g.nk; ++k) {
           const double* cf = coef + ((size_t)cls * PDE_NOFF + g.kidx[k]) * (NC * NC);
           const long long off = g.koff[k];
-          double xv[NC];
+          double xk[NC];
 #pragma unroll
-          for (int j = 0; j < NC; ++j) xv[j] = a.x[idx + off + j * g.comp_stride];
+          for (int j = 0; j < NC; ++j) xk[j] = a.x[idxl + off + j * g.comp_stride];
 #pragma unroll
           for (int i = 0; i < NC; ++i)
 #pragma unroll
-            for (int j = 0; j < NC; ++j) acc[i] = fma(__ldg(cf + i * NC + j), xv[j], acc[i]);
+            for (int j = 0; j < NC; ++j) acc[i] = fma(__ldg(cf + i * NC + j), xk[j], acc[i]);
         }
       }
       const double ld = a.b ? 0.0 : __ldg(load + cls);
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
-        const long long ii = idx + i * g.comp_stride;
-        const double B = a.b ? a.b[ii] : a.bconst[i] * ld;
+        const double B = a.b ? bv[i] : a.bconst[i] * ld;
         if (CHEBY) {
-          const double xo = a.x[ii];
-          const double dprev = a.prev_mode == 1 ? xo - a.xprev[ii] : (a.prev_mode == 2 ? xo : 0.0);
+          const double dprev = a.prev_mode == 1 ? xo[i] - pv[i] : (a.prev_mode == 2 ? xo[i] : 0.0);
           const double dn = a.c1 * dprev + a.c2 * __ldg(dinv + cls * NC + i) * (B - acc[i]);
-          const double yv = xo + dn;
-          a.y[ii] = yv;
+          const double yv = xo[i] + dn;
+          (a.y + i * g.comp_stride)[idxl] = yv;
           acc_xy = fma(B, yv, acc_xy);
         } else {
           const double yv = a.bscale * B + a.ascale * acc[i];
-          if (a.y) a.y[ii] = yv;
-          acc_xy = fma(a.x[ii], yv, acc_xy);
+          if (a.y) (a.y + i * g.comp_stride)[idxl] = yv;
+          acc_xy = fma(xo[i], yv, acc_xy);
           acc_yy = fma(yv, yv, acc_yy);
         }
       }
     }
-    if (FULL) __syncthreads();   // the flags and the table rows are rebuilt by the next trip
   }
-  if (a.do_reduce) {
+  if (a.do_reduce && a.defer) {
+    // deferred: plain block sums, picked up by the finalize of the sweep kernel that follows
+    __shared__ double sm2[2][FACE_NT / 32];
+    double v[2] = {acc_xy, acc_yy};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_down_sync(0xffffffffu, v[i], o);
+      if ((threadIdx.x & 31) == 0) sm2[i][threadIdx.x >> 5] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < FACE_NT / 32; ++w) t += sm2[threadIdx.x][w];
+      a.defer[(size_t)blockIdx.x * RED_MAX_VALS + threadIdx.x] = t;
+    }
+  } else if (a.do_reduce) {
     if (CHEBY) {
       double v[1] = {acc_xy};
       block_reduce_finalize<1, true>(v, red, red_out);
@@ -379,17 +430,21 @@ k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, co
   }
 }
 
-int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
+int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, int* defer_blocks) {
+  if (defer_blocks) *defer_blocks = 0;
   if (a.cheby == 2) PDE_FAIL("fused first sweeps need a uniform diagonal (no natural faces)");
   FaceSet fs;
   memset(&fs, 0, sizeof(fs));
+  long long ntiles = 0;
   const int n0 = g.nn[0], n1 = g.nn[1];
   auto add = [&](int axis, int fixed, int lo0, int c0, int lo1, int c1) {
     if (c0 <= 0 || c1 <= 0) return;
     const int f = fs.nface++;
     fs.axis[f] = axis; fs.fixed[f] = fixed;
     fs.lo[f][0] = lo0; fs.cnt[f][0] = c0; fs.lo[f][1] = lo1; fs.cnt[f][1] = c1;
-    fs.start[f + 1] = fs.start[f] + (long long)c0 * c1;
+    fs.tiles0[f] = (c0 + FACE_TU - 1) / FACE_TU;
+    ntiles += (long long)fs.tiles0[f] * ((c1 + FACE_TV - 1) / FACE_TV);
+    fs.tstart[f + 1] = (int)(ntiles > RED_MAX_BLOCKS ? RED_MAX_BLOCKS + 1LL : ntiles);
   };
   // a face whose Dirichlet flag is set contributes no free rows, except that the reference's "other_faces"
   // rule (side_excl) leaves the x-end columns of side faces free: keep such faces listed
@@ -407,19 +462,18 @@ int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op
     if (g.z0 == 0 && (!bc.on[4] || keep_all)) add(2, 0, 1, n0 - 2, ylo, ycnt);
     if (g.z0 + g.nzl == g.nzg && (!bc.on[5] || keep_all)) add(2, g.nzl - 1, 1, n0 - 2, ylo, ycnt);
   }
-  const long long total = fs.start[fs.nface];
-  if (total == 0) return 0;
+  if (ntiles == 0) return 0;
+  if (ntiles > RED_MAX_BLOCKS) PDE_FAIL("face grid exceeds the reduction buffer");
   StencilDev sd;
   sd.x = a.x; sd.b = a.b; sd.y = a.y; sd.xprev = a.xprev; sd.prev_mode = a.prev_mode;
   for (int i = 0; i < 3; ++i) sd.bconst[i] = a.bconst[i];
   sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2; sd.s0 = a.s0;
   sd.do_reduce = a.reduce_slot_xy >= 0;
   sd.first2 = 0;
-  // one node per thread while the grid fits the reduction buffer: the kernel is latency-bound, not bandwidth-bound
-  long long nb = (total + FACE_NT - 1) / FACE_NT;
-  if (nb > RED_MAX_BLOCKS) nb = RED_MAX_BLOCKS;
-  const int blocks = (int)nb;
-  bool full = g.dim == 3 && g.nk == PDE_NOFF;
+  sd.defer = (defer_blocks && sd.do_reduce) ? c->face_partials : nullptr;
+  const int blocks = (int)ntiles;
+  if (sd.defer) *defer_blocks = blocks;
+  bool full = g.dim == 3 && g.nk == PDE_NOFF && g.comp_stride * op.ncomp < (1LL << 31);
   for (int k = 0; full && k < PDE_NOFF; ++k) full = g.kidx[k] == k;
   double* out = sd.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
 #define FACE_LAUNCH(CH, FU)                                                                                      \
