@@ -111,6 +111,62 @@ for kind, mn, mL, faces in (("heat", [96, 40, 32 * world], [1.0, 0.5, 0.4 * worl
         print(f"[mgpu] manufactured {kind} {mn} x{world}: rel-L2 {err:.2e} iters {mst['iters_total']} levels {mst['levels']} "
               f"true relres {mst['true_relres']:.1e}", flush=True)
         ok = ok and err <= 1e-8 and mst["converged"] == 1 and mst["levels"] > 1
+# ---- cubic grids: the coarse levels end up with fewer planes than ranks (replicated levels below the slab levels) ----
+for cn in ([64, 64, 64], [96, 96, 96]):
+    if cn[2] % world:
+        continue
+    hs = _lib.HeatStepper(ctx, 3, cn, [1.0, 1.0, 1.0], 1.0, 0.01, T_initial=20.0, bc=_lib.make_bc({f: 0.0 for f in range(6)}),
+                          opts=_lib.make_opts(rtol=1e-10, precond="gmg"))
+    st = hs.step(2)
+    u = np.empty(hs.nloc)
+    hs.get_state(u)
+    hs.close()
+    full = gather(u)
+    if rank == 0:
+        # the N-GPU result against the 1-GPU result of the same global problem
+        c1 = _lib.Context(local)
+        h1 = _lib.HeatStepper(c1, 3, cn, [1.0, 1.0, 1.0], 1.0, 0.01, T_initial=20.0, bc=_lib.make_bc({f: 0.0 for f in range(6)}),
+                              opts=_lib.make_opts(rtol=1e-10, precond="gmg"))
+        s1 = h1.step(2)
+        u1 = np.empty(h1.nloc)
+        h1.get_state(u1)
+        h1.close()
+        d = fo.rel_l2(full, u1)
+        print(f"[mgpu] heat {cn} x{world} vs 1 GPU: rel-L2 {d:.2e} (iters {st['iters_total']} vs {s1['iters_total']}, "
+              f"levels {st['levels']}, true relres {st['true_relres']:.1e})", flush=True)
+        ok = ok and d <= 1e-9 and st["converged"] == 1 and st["true_relres"] <= 1e-9
+    dist.barrier()   # the other ranks must not start spinning on rank 0's halo flags while it solves alone
+# elasticity, N GPUs against 1 GPU on the same global cantilever (sizes that take k_elast3d and the face-row kernel)
+en2, eL2 = [64, 16, 16 * world], [1.0, 0.25, 0.25 * world]
+
+
+def elast_solve(cx, rk, wd):
+    z0_, nzl_, _ = _lib.slab_partition(3, en2, rk, wd)
+    nl = (en2[0] + 1) * (en2[1] + 1) * nzl_
+    q = _lib.ElastParams()
+    q.dim = 3
+    q.n = _lib.i3(en2)
+    q.L = _lib.d3(eL2)
+    q.E, q.nu = 210e9, 0.3
+    q.body = _lib.d3([0.0, 0.0, -76518.0], 0.0)
+    q.quantity, q.plane_stress, q.area = 0, 0, 1.0
+    v, dd = np.empty(nl), np.empty((nl, 3))
+    s_, p_ = _lib.Stats(), _lib.Stats()
+    _lib.check(_lib.lib().pde_elasticity_solve(cx.handle, C.byref(q), C.byref(_lib.make_opts(rtol=1e-10, precond="gmg")),
+                                               _lib.ptr(v), _lib.ptr(dd), C.byref(s_), C.byref(p_)))
+    return v, dd, s_
+
+
+vmN, dN, sN = elast_solve(ctx, rank, world)
+vmN, dN = gather(vmN), gather(dN.ravel())
+if rank == 0:
+    c1 = _lib.Context(local)
+    vm1, d1, s1 = elast_solve(c1, 0, 1)
+    e1, e2 = fo.rel_l2(vmN, vm1), fo.rel_l2(dN, d1.ravel())
+    print(f"[mgpu] elasticity {en2} x{world} vs 1 GPU: von Mises rel-L2 {e1:.2e}, displacement rel-L2 {e2:.2e} "
+          f"(iters {sN.iters_total} vs {s1.iters_total}, true relres {sN.true_relres:.1e})", flush=True)
+    ok = ok and e1 <= 1e-8 and e2 <= 1e-8 and sN.converged == 1
+dist.barrier()
 # ---- halo exchange self-check: sizes grow (the mailboxes are re-mapped collectively), 1 / 2 planes, 1 / 3 components
 for n_h in ([40, 24, 16 * world], [96, 80, 24 * world], [512, 512, 8 * world]):
     for ncomp_h, depth_h in ((1, 1), (1, 2), (3, 1), (3, 2)):
