@@ -612,9 +612,12 @@ extern "C" int pde_heat_solve(pde_ctx* c, const pde_heat_params* p, const pde_so
     if ((rc = pipe_push_snapshot(s, values_out))) break;
     times_out[snap++] = 0.0;
     const int stride = p->snapshot_stride > 0 ? p->snapshot_stride : 1;
+    const int verify = s->o.verify_residual;
     for (int step = 0; step < p->num_steps; ++step) {
       pde_stats st;
+      s->o.verify_residual = step == p->num_steps - 1 ? verify : -1;   // true residual of the LAST step only
       if ((rc = pde_heat_step(s, 1, &st))) break;
+      acc.true_relres = st.true_relres;
       acc.iters_total += st.iters_total;
       acc.solves += st.solves;
       acc.converged &= st.converged;

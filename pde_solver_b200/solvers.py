@@ -118,7 +118,8 @@ def _heat_streaming(ctx, p, dim, n, L, rtol, precond, u0, writer):
             for k in ("iters_total", "solves", "solve_ms", "launches"):
                 acc[k] += d[k]
             acc["converged"] &= d["converged"]
-            acc.update(ndofs=d["ndofs"], levels=d["levels"], final_relres=d["final_relres"], setup_ms=d["setup_ms"])
+            acc.update(ndofs=d["ndofs"], levels=d["levels"], final_relres=d["final_relres"], setup_ms=d["setup_ms"],
+                       true_relres=d["true_relres"])
             if (step + 1) % stride == 0:
                 _lib.check(_lib.lib().pde_heat_get_state(st_h, _lib.ptr(buf.array)))
                 times.append((step + 1) * p.dt)
