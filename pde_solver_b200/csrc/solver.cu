@@ -556,13 +556,59 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
                   lean[l] != 0));
     return 0;
   };
-  // the part below level 0: fixed kernels, fixed arguments
-  auto middle = [&]() -> int {
-    PDE_OK(restrict_to(0));
-    for (int l = 1; l < nl - 1; ++l) { PDE_OK(down(l)); PDE_OK(restrict_to(l)); }
+  // The V-cycle on levels >= R (level R's right-hand side is ready): fixed kernels with fixed arguments and, when level R
+  // is replicated (or on a single GPU), no communication at all - 40-60 launch-bound kernels that are captured into a
+  // CUDA graph on the second cycle and replayed afterwards.
+  auto sub = [&](int R) -> int {
+    for (int l = R; l < nl - 1; ++l) { PDE_OK(down(l)); PDE_OK(restrict_to(l)); }
     PDE_OK(coarsest());
-    for (int l = nl - 2; l >= 1; --l) { PDE_OK(prolong_into(l)); PDE_OK(post(l)); }
-    PDE_OK(prolong_into(0));
+    for (int l = nl - 2; l >= R; --l) { PDE_OK(prolong_into(l)); PDE_OK(post(l)); }
+    return 0;
+  };
+  // single GPU: R = 1 (the restriction out of level 0 and the prolongation back into it ride in the graph too);
+  // slabs: R = the first replicated level (the levels above it exchange halos through flag-waiting kernels and NCCL,
+  // which stay outside the graph)
+  int R = 1;
+  if (c->world > 1) {
+    R = nl;
+    for (int l = 1; l < nl; ++l)
+      if (lv[l]->replicated) { R = l; break; }
+  }
+  const bool solo = c->world == 1;
+  auto graph_part = [&]() -> int {
+    if (solo) { PDE_OK(restrict_to(0)); PDE_OK(sub(1)); PDE_OK(prolong_into(0)); return 0; }
+    // the prolongation out of level R rides along: it is the only reader of level R's result, whose buffer (the
+    // ping-pong state after the smoother swaps) is only known while the sub-cycle is issued, not while it is replayed
+    PDE_OK(sub(R));
+    return prolong_into(R - 1);
+  };
+  auto run_graph_part = [&]() -> int {
+    if (gstate == 2) {
+      CUDA_OK(cudaGraphLaunch(gexec, c->stream));
+      c->launches += gnodes;
+    } else if (gstate == 1) {
+      // second cycle: every static set-up (function attributes, tensor maps) happened in the first one
+      const long long l0 = c->launches;
+      CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = graph_part();
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ec = cudaStreamEndCapture(c->stream, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ec != cudaSuccess || !graph) { cudaGetLastError(); gstate = -1; PDE_OK(graph_part()); }
+      else {
+        gnodes = c->launches - l0;
+        const cudaError_t ei = cudaGraphInstantiate(&gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { cudaGetLastError(); gexec = nullptr; gstate = -1; c->launches = l0; PDE_OK(graph_part()); }
+        else {
+          gstate = 2;
+          CUDA_OK(cudaGraphLaunch(gexec, c->stream));   // the capture did not execute anything
+        }
+      }
+    } else {
+      PDE_OK(graph_part());
+      if (gstate == 0) gstate = 1;
+    }
     return 0;
   };
   if (nl == 1) {
@@ -571,33 +617,21 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
     return 0;
   }
   static const int graph_env = getenv("PDE_B200_MG_GRAPH") ? atoi(getenv("PDE_B200_MG_GRAPH")) : 1;
-  if (gstate == 0 && !(graph_env && c->world == 1 && nl >= 3)) gstate = -1;
+  if (gstate == 0 && !(graph_env && (solo ? nl >= 3 : nl - R >= 2))) gstate = -1;
   PDE_OK(down(0));
-  if (gstate == 2) {
-    CUDA_OK(cudaGraphLaunch(gexec, c->stream));
-    c->launches += gnodes;
-  } else if (gstate == 1) {
-    // second cycle: every static set-up (function attributes, tensor maps) happened in the first one
-    const long long l0 = c->launches;
-    CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = middle();
-    cudaGraph_t graph = nullptr;
-    const cudaError_t ec = cudaStreamEndCapture(c->stream, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ec != cudaSuccess || !graph) { cudaGetLastError(); gstate = -1; PDE_OK(middle()); }
-    else {
-      gnodes = c->launches - l0;
-      const cudaError_t ei = cudaGraphInstantiate(&gexec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ei != cudaSuccess) { cudaGetLastError(); gexec = nullptr; gstate = -1; c->launches = l0; PDE_OK(middle()); }
-      else {
-        gstate = 2;
-        CUDA_OK(cudaGraphLaunch(gexec, c->stream));   // the capture did not execute anything
-      }
-    }
+  if (solo) {
+    PDE_OK(run_graph_part());
   } else {
-    PDE_OK(middle());
-    if (gstate == 0) gstate = 1;
+    PDE_OK(restrict_to(0));
+    for (int l = 1; l < R && l < nl - 1; ++l) { PDE_OK(down(l)); PDE_OK(restrict_to(l)); }
+    if (R < nl) {
+      PDE_OK(run_graph_part());
+      for (int l = R - 1; l >= 1; --l) { PDE_OK(post(l)); PDE_OK(prolong_into(l - 1)); }
+    } else {          // no replicated level: the coarsest level is a slab level
+      PDE_OK(coarsest());
+      for (int l = nl - 2; l >= 1; --l) { PDE_OK(prolong_into(l)); PDE_OK(post(l)); }
+      PDE_OK(prolong_into(0));
+    }
   }
   PDE_OK(post(0));
   *z_out = cur[0];
