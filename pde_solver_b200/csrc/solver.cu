@@ -12,6 +12,8 @@
 
 int launch_stencil_generic(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a);
 int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, bool* handled);
+int launch_heat_post2(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, double* y, double c2_0,
+                      double c1_1, double c2_1, int dot_slot, bool* handled);
 
 int launch_stencil(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
   if (a.variant == 0) {
@@ -460,7 +462,8 @@ static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double*
       PDE_OK(comm_halo_exchange(c, L.op.g, 1, *cur, PDE_NG));
       PDE_OK(comm_halo_exchange(c, L.op.g, 1, const_cast<double*>(b), 1));
     }
-    PDE_OK(launch_post2(c, L.op.g, L.op.bc, L.op.dev, *cur, b, *oth, c2a, c1b, c2b, dot_slot, &handled));
+    PDE_OK(launch_heat_post2(c, L.op.g, L.op.dev, *cur, b, *oth, c2a, c1b, c2b, dot_slot, &handled));
+    if (!handled) PDE_OK(launch_post2(c, L.op.g, L.op.bc, L.op.dev, *cur, b, *oth, c2a, c1b, c2b, dot_slot, &handled));
     if (handled) {
       std::swap(*cur, *oth);
       if (dot_slot >= 0 && dot_done) *dot_done = true;
