@@ -69,7 +69,15 @@ def _save(field: TimeSeriesField, data_dir: str, stem: str, tag: Optional[str] =
     data_path = Path(data_dir)
     data_path.mkdir(parents=True, exist_ok=True)
     if writer is not None:
-        field.meta["snapshots_file"] = writer.close()
+        # steady solves and the cylinder / composite-core branch never stream: do not publish an empty series
+        written = len(writer.times)
+        path = writer.close()
+        if written > 0:
+            field.meta["snapshots_file"] = path
+        else:
+            for leftover in (path, os.path.splitext(path)[0] + ".bin"):
+                if os.path.exists(leftover):
+                    os.remove(leftover)
     filepath = data_path / f"{stem}_{tag or uuid.uuid4().hex[:8]}.pkl"
     with open(filepath, "wb") as f:
         pickle.dump(field, f, protocol=pickle.HIGHEST_PROTOCOL)

@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-from . import _lib, mesh
+from . import _lib, mesh, multi
 from .fields import TimeSeriesField
 
 # above this many stored values the result keeps NumPy arrays instead of nested Python lists
@@ -82,10 +82,15 @@ def _heat(dim, L, n, diffusivity, T_initial, dt, num_steps, steady, source_type,
     if stream_to is not None and not steady:
         return _heat_streaming(ctx, p, dim, n, L, rtol, precond, u0, stream_to)
     nsnap = 1 if steady else 1 + int(num_steps) // max(1, int(snapshot_stride))
+    o = _lib.make_opts(rtol=rtol, precond=precond)
+    if dim == 3 and u0 is None and multi.usable(int(n[2])):
+        # PDE_B200_GPUS=N: the same call on N z-slabs, one worker process per GPU (multi.py)
+        stats, values, times = multi.heat_solve(p, o, nsnap, nv)
+        _record(stats, "heat solve")
+        return mesh.coordinates(dim, n, L, ctx), values, times
     values = np.empty((nsnap, nv), dtype=np.float64)
     times = np.empty(nsnap, dtype=np.float64)
     st = _lib.Stats()
-    o = _lib.make_opts(rtol=rtol, precond=precond)
     u0a = np.ascontiguousarray(u0, dtype=np.float64) if u0 is not None else None
     _lib.check(_lib.lib().pde_heat_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(u0a), _lib.ptr(values),
                                          _lib.ptr(times), C.byref(st)))
@@ -302,10 +307,14 @@ def _elasticity(dim, L, n, E, nu, body, quantity, plane_stress=True, area=1.0, r
     p.plane_stress = 1 if plane_stress else 0
     p.area = float(area)
     nv, _ = _lib.mesh_counts(dim, n)
+    o = _lib.make_opts(rtol=rtol, precond=precond)
+    if dim == 3 and multi.usable(int(n[2])):
+        stats, pstats, out, disp = multi.elasticity_solve(p, o, nv, want_displacement)
+        _record(stats, "elasticity solve", projection=pstats)
+        return mesh.coordinates(dim, n, L, ctx), out, disp
     out = np.empty(nv, dtype=np.float64)
     disp = np.empty((nv, dim), dtype=np.float64) if want_displacement else None
     st, sp = _lib.Stats(), _lib.Stats()
-    o = _lib.make_opts(rtol=rtol, precond=precond)
     _lib.check(_lib.lib().pde_elasticity_solve(ctx.handle, C.byref(p), C.byref(o), _lib.ptr(out), _lib.ptr(disp),
                                                C.byref(st), C.byref(sp)))
     _record(st.as_dict(), "elasticity solve", projection=sp.as_dict())

@@ -695,3 +695,39 @@ def test_heat_superposition_at_128_cubed(P):
     # the boundary nodes of the initial snapshot carry T_boundary in every run: a has 0 there, b has 5, c has 5
     for k in range(1, 4):
         assert fo.rel_l2(c[k], a[k] + b[k]) <= 10 * TOL, k
+
+
+# ---------------------------------------------------------------- the MCP tools on several GPUs from ONE process
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs")
+def test_mcp_tools_use_two_gpus_from_one_process(monkeypatch, tmp_path):
+    """PDE_B200_GPUS=2: solve_heat_3D / solve_elasticity_3D_static (the functions the orchestrator calls in its single
+    tool process, multi_agent_orchestrator.py:70-78) run slab-partitioned on two GPUs through spawned worker ranks and
+    return the single-GPU arrays."""
+    import pickle
+
+    import fenics_mcp_server as srv
+    monkeypatch.setenv("PDE_B200_GPUS", "2")
+    r = srv.solve_heat_3D(1.0, 1.0, 0.5, 32, 32, 16, 1.0, 0.0, 20.0, 0.01, 3, data_dir=str(tmp_path))
+    f = pickle.load(open(r.data_file, "rb"))
+    ref = fo.solve_heat(3, [1, 1, 0.5], [32, 32, 16], 1.0, T_initial=20.0, dt=0.01, num_steps=3)
+    assert np.array_equal(np.asarray(f.coords), ref.coords)
+    for k in range(4):
+        assert fo.rel_l2(np.asarray(f.values[k]), ref.values[k]) <= TOL
+    import pde_solver_b200 as P
+    assert P.last_stats().get("gpus") == 2
+    r = srv.solve_elasticity_3D_static(1.0, 0.2, 0.2, 40, 8, 8, 210e9, 0.3, 0.0, 0.0, -76518.0, "stress",
+                                       data_dir=str(tmp_path))
+    g = pickle.load(open(r.data_file, "rb"))
+    ref2 = fo.solve_elasticity(3, [1, 0.2, 0.2], [40, 8, 8], 210e9, 0.3, body=[0, 0, -76518.0])
+    assert fo.rel_l2(np.asarray(g.values[0]), ref2.values[0]) <= TOL
+    assert P.last_stats().get("gpus") == 2
+    from pde_solver_b200 import multi
+    multi.pool().close()
