@@ -3,7 +3,9 @@
 Mirrors what the reference obtains from DOLFIN (fenics_mcp_server.py:229-230, 369-370, 533-535,
 1649-1650, 1804-1805, 233-241, 373-376, 606-628): IntervalMesh / RectangleMesh("right") / BoxMesh
 vertex coordinates and connectivity, FunctionSpace / VectorFunctionSpace cell-dof tables, and the
-topological DirichletBC vertex sets.  Numbering is DOLFIN's with reorder_dofs_serial=False."""
+topological DirichletBC vertex sets.  Numbering is DOLFIN's with reorder_dofs_serial=False; DOLFIN's default
+(reorder_dofs_serial=True: a graph reordering of the dofs that cannot be derived from anything in the reference) can be
+plugged in as a permutation, see set_dof_permutation."""
 import ctypes as C
 
 import numpy as np
@@ -13,6 +15,41 @@ from . import _lib
 
 def _n3(n):
     return list(n) + [0] * (3 - len(n))
+
+
+# ---- pluggable dof numbering ---------------------------------------------------------------------
+# vertex_of_dof[d] = natural (x fastest) vertex index that scalar dof d sits on; for DOLFIN this is
+# dof_to_vertex_map(FunctionSpace(mesh, "P", 1)) - tests/golden/make_fenics_golden.py records it for both settings of
+# reorder_dofs_serial.  Registered per mesh; every exported array (coords, values, cell-dof tables, Dirichlet masks) of
+# that mesh then comes out in the plugged numbering.  Nothing on the device changes: the solver keeps natural order.
+_dof_perm = {}
+
+
+def _key(dim, n):
+    return (int(dim),) + tuple(int(v) for v in list(n)[:dim])
+
+
+def set_dof_permutation(dim, n, vertex_of_dof):
+    """Register (or, with None, remove) the dof numbering of the P1 space on the mesh (dim, n)."""
+    if vertex_of_dof is None:
+        _dof_perm.pop(_key(dim, n), None)
+        return
+    v = np.asarray(vertex_of_dof, dtype=np.int64)
+    nv, _ = _lib.mesh_counts(dim, n)
+    if v.shape != (nv,) or not np.array_equal(np.sort(v), np.arange(nv)):
+        raise ValueError("vertex_of_dof must be a permutation of the mesh vertices")
+    _dof_perm[_key(dim, n)] = v
+
+
+def dof_permutation(dim, n):
+    """vertex_of_dof of the mesh, or None for the natural numbering."""
+    return _dof_perm.get(_key(dim, n))
+
+
+def to_dof_order(dim, n, a, axis=-1):
+    """Reorder the vertex axis of `a` (natural order) into the plugged dof numbering."""
+    v = dof_permutation(dim, n)
+    return a if v is None else np.take(a, v, axis=axis)
 
 
 def coordinates(dim, n, L, ctx=None):
@@ -50,6 +87,17 @@ def cell_dofs(dim, n, ncomp=1, layout="blocked", ctx=None):
     out = np.empty((nc, ncomp * (dim + 1)), dtype=np.int32)
     _lib.check(_lib.lib().pde_dofmap_cells(ctx.handle, int(dim), _lib.i3(n), int(ncomp),
                                             0 if layout == "blocked" else 1, _lib.ptr(out)))
+    v = dof_permutation(dim, n)
+    if v is not None:       # natural dof (c, vertex) -> plugged scalar numbering of its vertex, same layout
+        nv = v.size
+        dof_of_vertex = np.empty(nv, dtype=np.int64)
+        dof_of_vertex[v] = np.arange(nv)
+        if layout == "blocked":
+            comp, vert = out // nv, out % nv
+            out = (comp * nv + dof_of_vertex[vert]).astype(np.int32)
+        else:
+            vert, comp = out // ncomp, out % ncomp
+            out = (dof_of_vertex[vert] * ncomp + comp).astype(np.int32)
     return out
 
 
@@ -61,7 +109,7 @@ def dirichlet(dim, n, bc, ctx=None):
     vals = np.empty(nv, dtype=np.float64)
     _lib.check(_lib.lib().pde_boundary_mask(ctx.handle, int(dim), _lib.i3(n), C.byref(bc), _lib.ptr(mask),
                                              _lib.ptr(vals)))
-    return mask, vals
+    return to_dof_order(dim, n, mask), to_dof_order(dim, n, vals)
 
 
 def heat_bc(dim, T_boundary=0.0, T_left=None, T_right=None, T_side=None):

@@ -46,7 +46,12 @@ def _embed3(coords, dim):
     return out
 
 
-def _finish(coords3, values, times, dim, meta, as_arrays):
+def _finish(coords3, values, times, dim, meta, as_arrays, n=None):
+    if n is not None and mesh.dof_permutation(dim, n) is not None:
+        # plugged dof numbering (mesh.set_dof_permutation): coordinates and values leave in that order, paired exactly
+        # as the reference pairs tabulate_dof_coordinates() with get_local()
+        coords3 = mesh.to_dof_order(dim, n, coords3, axis=0)
+        values = mesh.to_dof_order(dim, n, values, axis=-1)
     if as_arrays is None:
         as_arrays = values.size > LIST_LIMIT
     if as_arrays:
@@ -169,7 +174,7 @@ def _solve_heat_2d_raw(Lx: float, Ly: float, nx: int, ny: int, diffusivity: floa
                                   bc, rtol, precond, snapshot_stride, u0, stream_to=stream_to)
     meta = {"name": "temperature", "unit": "°C", "pde": "heat", "coordinate_system": "cartesian", "Lx": Lx,
             "Ly": Ly, "source_type": source_type, "source_value": source_value, "steady": steady}
-    return _finish(_embed3(coords, 2), values, times, 2, meta, as_arrays)
+    return _finish(_embed3(coords, 2), values, times, 2, meta, as_arrays, n=[nx, ny])
 
 
 def _solve_heat_3d_raw(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: int, diffusivity: float,
@@ -206,7 +211,7 @@ def _solve_heat_3d_raw(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: in
     else:
         meta["T_boundary"] = T_boundary
     meta["diffusivity"] = diffusivity
-    return _finish(coords, values, times, 3, meta, as_arrays)
+    return _finish(coords, values, times, 3, meta, as_arrays, n=[nx, ny, nz])
 
 
 def _heat_3d_special(Lx, Ly, Lz, nx, ny, nz, diffusivity, T_boundary, T_initial, dt, num_steps, steady, source_type,
@@ -348,7 +353,7 @@ def _solve_elasticity_2d_static(Lx: float, Ly: float, nx: int, ny: int, E: float
     name, unit = ("von_mises_strain", "-") if quantity == "strain" else ("von_mises_stress", "Pa")
     meta = {"name": name, "unit": unit, "pde": "elasticity_2d", "Lx": Lx, "Ly": Ly, "E": E, "nu": nu,
             "body_fx": body_fx, "body_fy": body_fy, "quantity": quantity, "plane_stress": plane_stress}
-    return _finish(_embed3(coords, 2), val[None, :], [0.0], 2, meta, as_arrays)
+    return _finish(_embed3(coords, 2), val[None, :], [0.0], 2, meta, as_arrays, n=[nx, ny])
 
 
 def _solve_elasticity_3d_static(Lx: float, Ly: float, Lz: float, nx: int, ny: int, nz: int, E: float, nu: float,
@@ -361,7 +366,7 @@ def _solve_elasticity_3d_static(Lx: float, Ly: float, Lz: float, nx: int, ny: in
     name, unit = ("von_mises_strain", "-") if quantity == "strain" else ("von_mises_stress", "Pa")
     meta = {"name": name, "unit": unit, "pde": "elasticity_3d", "Lx": Lx, "Ly": Ly, "Lz": Lz, "E": E, "nu": nu,
             "body_fx": body_fx, "body_fy": body_fy, "body_fz": body_fz, "quantity": quantity}
-    return _finish(coords, val[None, :], [0.0], 3, meta, as_arrays)
+    return _finish(coords, val[None, :], [0.0], 3, meta, as_arrays, n=[nx, ny, nz])
 
 
 # ----------------------------------------------------------------------------------------------------------

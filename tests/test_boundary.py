@@ -244,3 +244,20 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
             assert C.sizeof(getattr(L, pairs[t[1]])) == int(t[2]), line
         else:
             assert getattr(getattr(L, pairs[t[1]]), t[2]).offset == int(t[3]), line
+
+
+def test_dof_permutation_hook_is_validated():
+    """mesh.set_dof_permutation: only true permutations of the mesh vertices are accepted; the
+    arrays it reorders are exercised on the GPU (tests/test_gpu_parity.py::test_dof_permutation_reorders_exports)."""
+    import pytest as _pt
+    from pde_solver_b200 import mesh
+    with _pt.raises(ValueError):
+        mesh.set_dof_permutation(2, [2, 2], [0, 1, 2])
+    with _pt.raises(ValueError):
+        mesh.set_dof_permutation(2, [2, 2], [0] * 9)
+    mesh.set_dof_permutation(2, [2, 2], list(range(9))[::-1])
+    assert mesh.dof_permutation(2, [2, 2])[0] == 8
+    a = np.arange(18).reshape(2, 9)
+    assert np.array_equal(mesh.to_dof_order(2, [2, 2], a), a[:, ::-1])
+    mesh.set_dof_permutation(2, [2, 2], None)
+    assert mesh.dof_permutation(2, [2, 2]) is None

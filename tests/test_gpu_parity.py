@@ -697,6 +697,28 @@ def test_heat_superposition_at_128_cubed(P):
         assert fo.rel_l2(c[k], a[k] + b[k]) <= 10 * TOL, k
 
 
+def test_dof_permutation_reorders_exports(P):
+    """Row a3: with a dof numbering plugged in (as DOLFIN's reorder_dofs_serial=True would give), coordinates, values,
+    cell-dof tables and Dirichlet masks leave in that numbering, still paired node by node."""
+    n, L = [6, 5], [1.0, 0.6]
+    rng = np.random.default_rng(3)
+    nv = 7 * 6
+    perm = rng.permutation(nv)
+    base = P._solve_heat_2d_raw(1.0, 0.6, 6, 5, 1.0, 0.0, 20.0, 0.01, 3, as_arrays=True)
+    cd0 = P.mesh.cell_dofs(2, n)
+    m0, _ = P.mesh.dirichlet(2, n, P._lib.make_bc({f: 0.0 for f in range(4)}))
+    P.mesh.set_dof_permutation(2, n, perm)
+    try:
+        f = P._solve_heat_2d_raw(1.0, 0.6, 6, 5, 1.0, 0.0, 20.0, 0.01, 3, as_arrays=True)
+        assert np.array_equal(f.coords, base.coords[perm]) and np.array_equal(f.values, base.values[:, perm])
+        cd = P.mesh.cell_dofs(2, n)
+        assert np.array_equal(perm[cd], cd0)                  # dof -> vertex through the plugged map gives the natural table
+        m1, _ = P.mesh.dirichlet(2, n, P._lib.make_bc({f: 0.0 for f in range(4)}))
+        assert np.array_equal(m1, m0[perm])
+    finally:
+        P.mesh.set_dof_permutation(2, n, None)
+
+
 # ---------------------------------------------------------------- the MCP tools on several GPUs from ONE process
 def _gpu_count():
     try:
