@@ -285,8 +285,11 @@ struct FaceSet {
 // read the coefficients as warp-uniform shared-memory broadcasts.
 // History on the cantilever faces of 1280x256x256 (1.38 M nodes): 141 us with per-node __ldg'ed coefficients and a
 // rolled offset loop, against 0.75 ms for the whole interior sweep.
+#ifndef FACE_MINB
+#define FACE_MINB 2
+#endif
 template <int NC, bool CHEBY, bool FULL>
-__global__ void __launch_bounds__(FACE_NT, FULL ? 2 : 1)
+__global__ void __launch_bounds__(FACE_NT, FULL ? FACE_MINB : 1)
 k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, const __grid_constant__ FaceSet fs,
             const double* __restrict__ coef, const double* __restrict__ dinv, const double* __restrict__ load,
             const __grid_constant__ StencilDev a, ReduceBuf red, double* red_out) {
