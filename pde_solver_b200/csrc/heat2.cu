@@ -37,7 +37,7 @@ struct HG {
   static constexpr int STAGE = XS + BS;
   static constexpr int RING = RA * CW;                                // one d0 plane of the grown tile
   static constexpr int NT = 2 * CW;
-  static constexpr size_t SMEM = ((size_t)H_STAGES * STAGE + 3 * RING) * sizeof(double) + H_STAGES * sizeof(uint64_t);
+  static constexpr size_t SMEM = ((size_t)H_STAGES * STAGE + 4 * RING) * sizeof(double) + H_STAGES * sizeof(uint64_t);   // four ring slots
 };
 
 struct H2Coef {
@@ -47,6 +47,10 @@ struct H2Args {
   double* y;
   double a0, a1, k1;     // k1 = 1 + c1 + a1 / a0
   int do_reduce;
+  // RR (residual + restriction): coarse right-hand side (plane 0 of the coarse slab / window) and its grid
+  double* yc;
+  int cnn0, cnn1, cnzl, cz0, cPX;
+  long long cplane;
 };
 struct H2Geom {
   int nn0, nn1, nzl, z0, nzg, PX;
@@ -80,7 +84,12 @@ __device__ __forceinline__ void h2_contrib(const H2Coef& C, const double (&V)[YS
   }
 }
 
-template <int CW, int YSB>
+// RR = false: the two post-smoothing sweeps (above).
+// RR = true : residual + restriction in one pass.  Stage A leaves r = m (b - A x) of the grown tile in the ring (a0 = 1) and
+//   nothing of it goes to HBM; on every even global plane stage B forms the coarse right-hand side at the even nodes of the
+//   tile, r(2X,2Y,2Z) + 1/2 (its 14 Kuhn neighbours), from the three ring planes around it: 17 B per fine dof (x, b in, 1/8
+//   out) instead of 24 (residual) + 9 (restriction).  Four ring slots: stage B reads the plane stage A wrote two steps ago.
+template <int CW, int YSB, bool RR>
 __global__ void __launch_bounds__(2 * CW, CW == 64 ? (YSB >= 4 ? 3 : (YSB == 3 ? 4 : 5)) : 6)
 k_heat_post2(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
              const __grid_constant__ H2Coef C, const __grid_constant__ H2Args a, const __grid_constant__ H2Geom ge,
@@ -90,7 +99,7 @@ k_heat_post2(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CU
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* const stage0 = reinterpret_cast<double*>(smem_raw);
   double* const ring0 = stage0 + H_STAGES * G::STAGE;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(ring0 + 3 * G::RING);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(ring0 + 4 * G::RING);
 
   const int t = threadIdx.x;
   const int item = blockIdx.x;
@@ -165,7 +174,7 @@ k_heat_post2(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CU
     const bool finA = i >= 2, finB = i >= 4;
     // what stage B needs of older pipeline stages is read before the barrier, so that stage i-2 can be refilled after it
     double xB0[YSB], bvB[YSB];
-    if (finB) {
+    if (!RR && finB) {
       const double* const sx2 = stage0 + ((i - 2) % H_STAGES) * G::STAGE + offxB;
       const double* const sb1 = stage0 + ((i - 1) % H_STAGES) * G::STAGE + offbB;
 #pragma unroll
@@ -187,16 +196,16 @@ k_heat_post2(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CU
       const int gz = pA + ge.z0;
       const bool zfree = gz >= 1 && gz <= ge.nzg - 2;
       const unsigned mA = zfree ? mAb : 0u;
-      double* const ds = ring0 + ((pA + 3) % 3) * G::RING + ringA;
+      double* const ds = ring0 + ((pA + 4) & 3) * G::RING + ringA;
       const double* const sb = sx + offbA;
 #pragma unroll
       for (int j = 0; j < YSA; ++j) ds[j * CW] = ((mA >> j) & 1u) ? a.a0 * (sb[j * G::BX] - aP[j]) : 0.0;
     }
     __syncthreads();   // plane pA of d0 is visible; stage i-2 (and the reads of stage B above) are done
     if (t == 0 && i + 2 < nplanes) issue(i + 2);
-    if (finA) {  // ---- stage B: plane pA of d0 ----
+    if (!RR && finA) {  // ---- stage B: plane pA of d0 ----
       double V[YSB + 2][3];
-      const double* const rp = ring0 + ((pA + 3) % 3) * G::RING + ringB;
+      const double* const rp = ring0 + ((pA + 4) & 3) * G::RING + ringB;
 #pragma unroll
       for (int r = 0; r < YSB + 2; ++r)
 #pragma unroll
@@ -204,11 +213,32 @@ k_heat_post2(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CU
           V[r][cc] = ((r == 0 && cc == 2) || (r == YSB + 1 && cc == 0)) ? 0.0 : rp[r * CW + cc];
       h2_contrib<YSB>(C, V, bP, b0, bM);
     }
-    if (finB) {
+    if (RR && finB) {
+      // ---- restriction: coarse plane Z = (pB + z0) / 2 from the residual planes pB-1, pB, pB+1 (= pA) of the ring ----
+      const int gz = pB + ge.z0;
+      const int Z = (gz >> 1) - a.cz0;
+      constexpr int NCX = G::TX / 2, NCY = G::TY / 2;
+      if (!(gz & 1) && Z >= 0 && Z < a.cnzl && t < NCX * NCY) {
+        const int cx = t % NCX, cy = t / NCX;
+        const int X = (x0 >> 1) + cx, Y = (y0 >> 1) + cy;
+        if (X < a.cnn0 && Y < a.cnn1) {
+          const int o = (1 + 2 * cy) * CW + 1 + 2 * cx;      // the fine node in the grown tile
+          const double* const r0 = ring0 + ((pB + 4) & 3) * G::RING + o;
+          const double* const rm = ring0 + ((pB + 3) & 3) * G::RING + o;
+          const double* const rp = ring0 + ((pB + 5) & 3) * G::RING + o;
+          const double nb = ((r0[1] + r0[-1]) + (r0[CW] + r0[-CW])) + ((r0[CW + 1] + r0[-CW - 1]) + (rp[0] + rm[0])) +
+                            ((rp[1] + rm[-1]) + (rp[CW] + rm[-CW])) + (rp[CW + 1] + rm[-CW - 1]);
+          const int cgz = gz >> 1;
+          const bool cfree = X >= 1 && X <= a.cnn0 - 2 && Y >= 1 && Y <= a.cnn1 - 2 && cgz >= 1 && cgz <= (ge.nzg >> 1) - 1;
+          a.yc[(long long)a.cPX * Y + a.cplane * Z + X] = cfree ? fma(0.5, nb, r0[0]) : 0.0;
+        }
+      }
+    }
+    if (!RR && finB) {
       const int gz = pB + ge.z0;
       const bool zfree = gz >= 1 && gz <= ge.nzg - 2;
       const unsigned mB = zfree ? mBb : 0u;
-      const double* const dso = ring0 + ((pB + 3) % 3) * G::RING + ringB + CW + 1;   // own node of stage-B row j: + j*CW
+      const double* const dso = ring0 + ((pB + 4) & 3) * G::RING + ringB + CW + 1;   // own node of stage-B row j: + j*CW
 #pragma unroll
       for (int j = 0; j < YSB; ++j) {
         const bool m = (mB >> j) & 1u;
@@ -232,9 +262,8 @@ k_heat_post2(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CU
   }
 }
 
-template <int CW, int YSB>
-int launch_t(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, double* y, double c2_0,
-             double c1_1, double c2_1, int dot_slot) {
+template <int CW, int YSB, bool RR>
+int launch_t(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, const H2Args& ha_in) {
   using G = HG<CW, YSB>;
   H2Geom ge;
   ge.nn0 = g.nn[0]; ge.nn1 = g.nn[1]; ge.nzl = g.nzl; ge.z0 = g.z0; ge.nzg = g.nzg; ge.PX = g.PX; ge.plane = g.plane;
@@ -248,7 +277,7 @@ int launch_t(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const
   ge.nzc = (g.nzl + ge.zc - 1) / ge.zc;
   const long long items = (long long)ge.ntx * ge.nty * ge.nzc;
   if (items > RED_MAX_BLOCKS) return 2;   // not applicable: the caller falls back
-  auto kern = k_heat_post2<CW, YSB>;
+  auto kern = k_heat_post2<CW, YSB, RR>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
@@ -262,16 +291,27 @@ int launch_t(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const
   const double* h = op.h_int;
   C.c0 = h[0]; C.cxp = h[1]; C.cxm = h[2]; C.cyp = h[3]; C.cym = h[4]; C.czp = h[5]; C.czm = h[6]; C.cxyp = h[7];
   C.cxym = h[8]; C.cxzp = h[9]; C.cxzm = h[10]; C.cyzp = h[11]; C.cyzm = h[12]; C.cdp = h[13]; C.cdm = h[14];
-  H2Args ha;
-  ha.y = y;
-  ha.a0 = c2_0 * op.h_dinv_int[0];
-  ha.a1 = c2_1 * op.h_dinv_int[0];
-  ha.k1 = 1.0 + c1_1 + ha.a1 / ha.a0;
-  ha.do_reduce = dot_slot >= 0;
-  kern<<<(unsigned)items, G::NT, G::SMEM, c->stream>>>(tmx, tmb, C, ha, ge, c->red, ha.do_reduce ? c->scal + dot_slot : nullptr);
+  kern<<<(unsigned)items, G::NT, G::SMEM, c->stream>>>(tmx, tmb, C, ha_in, ge, c->red, ha_in.do_reduce ? c->scal + ha_in.do_reduce - 1 : nullptr);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+bool heat2_applicable(const Grid& g, const OpDev& op) {
+  static const int off = env_int("PDE_B200_NO_HEAT2", 0);
+  if (off) return false;
+  if (g.dim != 3 || g.nk != PDE_NOFF || op.ncomp != 1 || !op.uniform_diag) return false;
+  return g.nn[0] >= 32 && g.nn[1] >= 8 && g.nzl >= 8;
+}
+
+template <bool RR>
+int dispatch(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, const H2Args& ha) {
+  static const int cw_env = env_int("PDE_B200_P2_CW", 0);
+  static const int ysb = env_int("PDE_B200_P2_YSB", 4);
+  const int cw = cw_env ? cw_env : (g.nn[0] >= 128 ? 64 : 32);
+  if (cw == 64 && ysb == 3) return launch_t<64, 3, RR>(c, g, op, x0, b, ha);
+  if (cw == 64) return launch_t<64, 4, RR>(c, g, op, x0, b, ha);
+  return launch_t<32, 4, RR>(c, g, op, x0, b, ha);
 }
 
 }  // namespace
@@ -280,19 +320,33 @@ int launch_t(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const
 int launch_heat_post2(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, double* y, double c2_0,
                       double c1_1, double c2_1, int dot_slot, bool* handled) {
   *handled = false;
-  static const int off = env_int("PDE_B200_NO_HEAT2", 0);
-  if (off) return 0;
-  if (g.dim != 3 || g.nk != PDE_NOFF || op.ncomp != 1 || !op.uniform_diag) return 0;
-  if (g.nn[0] < 32 || g.nn[1] < 8 || g.nzl < 8) return 0;
-  if (!(c2_0 * op.h_dinv_int[0] > 0.0)) return 0;
-  static const int cw_env = env_int("PDE_B200_P2_CW", 0);
-  const int cw = cw_env ? cw_env : (g.nn[0] >= 128 ? 64 : 32);
-  static const int ysb = env_int("PDE_B200_P2_YSB", 4);
-  int rc;
-  if (cw == 64 && ysb == 3) rc = launch_t<64, 3>(c, g, op, x0, b, y, c2_0, c1_1, c2_1, dot_slot);
-  else if (cw == 64 && ysb == 2) rc = launch_t<64, 2>(c, g, op, x0, b, y, c2_0, c1_1, c2_1, dot_slot);
-  else if (cw == 64) rc = launch_t<64, 4>(c, g, op, x0, b, y, c2_0, c1_1, c2_1, dot_slot);
-  else rc = launch_t<32, 4>(c, g, op, x0, b, y, c2_0, c1_1, c2_1, dot_slot);
+  if (!heat2_applicable(g, op) || !(c2_0 * op.h_dinv_int[0] > 0.0)) return 0;
+  H2Args ha{};
+  ha.y = y;
+  ha.a0 = c2_0 * op.h_dinv_int[0];
+  ha.a1 = c2_1 * op.h_dinv_int[0];
+  ha.k1 = 1.0 + c1_1 + ha.a1 / ha.a0;
+  ha.do_reduce = dot_slot >= 0 ? dot_slot + 1 : 0;   // slot + 1 (0: none)
+  const int rc = dispatch<false>(c, g, op, x0, b, ha);
+  if (rc == 0) *handled = true;
+  return rc == 2 ? 0 : rc;
+}
+
+// Residual of level gf and its restriction into the coarse grid gc (a slab, or this rank's window of a replicated
+// level) in one pass: bcoarse = R (b - A x), the fine residual is never stored.  Needs two valid halo planes of x and
+// one of b on slab runs (the lean halo scheme provides them).
+int launch_heat_resid_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const OpDev& op, const double* x, const double* b,
+                               double* bcoarse, bool* handled) {
+  *handled = false;
+  static const int off = env_int("PDE_B200_NO_RR", 0);
+  if (off || !heat2_applicable(gf, op)) return 0;
+  // nested grids, slab windows that nest too (rank r owns coarse planes z0/2 ...)
+  if (gf.nc[0] != 2 * gc.nc[0] || gf.nc[1] != 2 * gc.nc[1] || gf.nc[2] != 2 * gc.nc[2] || gf.z0 != 2 * gc.z0) return 0;
+  H2Args ha{};
+  ha.a0 = 1.0;
+  ha.yc = bcoarse;
+  ha.cnn0 = gc.nn[0]; ha.cnn1 = gc.nn[1]; ha.cnzl = gc.nzl; ha.cz0 = gc.z0; ha.cPX = gc.PX; ha.cplane = gc.plane;
+  const int rc = dispatch<true>(c, gf, op, x, b, ha);
   if (rc == 0) *handled = true;
   return rc == 2 ? 0 : rc;
 }

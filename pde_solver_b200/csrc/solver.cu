@@ -14,6 +14,8 @@ int launch_stencil_generic(pde_ctx* c, const Grid& g, const BcDev& bc, const OpD
 int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, bool* handled);
 int launch_heat_post2(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, double* y, double c2_0,
                       double c1_1, double c2_1, int dot_slot, bool* handled);
+int launch_heat_resid_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const OpDev& op, const double* x, const double* b,
+                               double* bcoarse, bool* handled);
 
 int launch_stencil(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a) {
   if (a.variant == 0) {
@@ -508,28 +510,34 @@ int Hierarchy::vcycle(pde_ctx* c, const Operator& fine, const double* b0, double
     MGLevel& L = *lv[l];
     const double* b = l == 0 ? b0 : L.b.p;
     PDE_OK(smooth(c, L, b, &cur[l], &oth[l], nu, true, ratio));   // exchanges one halo plane of b (fused first sweeps)
-    StencilArgs a;
-    a.x = cur[l]; a.b = b; a.y = L.r.p; a.bscale = 1.0; a.ascale = -1.0;
-    a.ghost_out = lean[l];
     if (c->world > 1) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, cur[l], lean[l] ? PDE_NG : 1));
-    PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
     return 0;
   };
+  // residual of level l and its restriction into level l+1.  Uniform-diagonal scalar levels do both in one pass
+  // (k_heat_post2<.., RR>: the fine residual never goes to HBM); otherwise residual kernel + restriction kernel.
   auto restrict_to = [&](int l) -> int {   // level l -> l+1
     MGLevel& L = *lv[l];
-    if (c->world > 1 && !lean[l]) PDE_OK(comm_halo_exchange(c, L.op.g, L.op.dev.ncomp, L.r.p));
     MGLevel& Lc = *lv[l + 1];
-    if (Lc.replicated && !L.replicated) {
-      // slab level -> replicated level: every rank restricts into its window of the global coarse array, the
-      // windows are disjoint, one all-reduce (sum with zeros) completes the array everywhere
-      const Grid& gc = Lc.op.g;
-      const int nc = L.op.dev.ncomp;
-      PDE_OK(launch_zero(c, gc, nc, Lc.b.p));
-      PDE_OK(launch_restrict(c, L.op.g, Lc.gslab, Lc.op.bc, nc, L.r.p, Lc.b.p + gc.plane * Lc.gslab.z0));
-      PDE_OK(comm_allreduce_buf(c, Lc.b.p, (size_t)(gc.comp_stride * (nc - 1) + gc.plane * gc.nzg)));
-    } else {
-      PDE_OK(launch_restrict(c, L.op.g, Lc.op.g, Lc.op.bc, L.op.dev.ncomp, L.r.p, Lc.b.p));
+    const double* b = l == 0 ? b0 : L.b.p;
+    const bool window = Lc.replicated && !L.replicated;
+    const Grid& gc = Lc.op.g;
+    const int nc = L.op.dev.ncomp;
+    // slab level -> replicated level: every rank restricts into its window of the global coarse array, the
+    // windows are disjoint, one all-reduce (sum with zeros) completes the array everywhere
+    if (window) PDE_OK(launch_zero(c, gc, nc, Lc.b.p));
+    const Grid& gct = window ? Lc.gslab : gc;
+    double* bct = window ? Lc.b.p + gc.plane * Lc.gslab.z0 : Lc.b.p;
+    bool fused = false;
+    if (c->world == 1 || lean[l]) PDE_OK(launch_heat_resid_restrict(c, L.op.g, gct, L.op.dev, cur[l], b, bct, &fused));
+    if (!fused) {
+      StencilArgs a;
+      a.x = cur[l]; a.b = b; a.y = L.r.p; a.bscale = 1.0; a.ascale = -1.0;
+      a.ghost_out = lean[l];
+      PDE_OK(launch_stencil(c, L.op.g, L.op.bc, L.op.dev, a));
+      if (c->world > 1 && !lean[l]) PDE_OK(comm_halo_exchange(c, L.op.g, nc, L.r.p));
+      PDE_OK(launch_restrict(c, L.op.g, gct, Lc.op.bc, nc, L.r.p, bct));
     }
+    if (window) PDE_OK(comm_allreduce_buf(c, Lc.b.p, (size_t)(gc.comp_stride * (nc - 1) + gc.plane * gc.nzg)));
     return 0;
   };
   auto coarsest = [&]() -> int {
