@@ -793,43 +793,53 @@ int launch_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcc
 
 // x_f += P x_c : fine node with parity pi is the midpoint of the coarse Kuhn edge ((f-pi)/2,(f+pi)/2)
 template <int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_prolong_add(const __grid_constant__ Grid gf, const __grid_constant__ Grid gc, const __grid_constant__ BcDev bcf,
               const double* __restrict__ xc, double* __restrict__ xf, int ghost) {
+  // flat over (row, node pair): two nodes (even ix, ix + 1) per thread, one 16-byte read-modify-write of the fine row
+  // and three coarse values (rows start 32-byte aligned; the node after the last one of a row is a pad column, which
+  // is written back unchanged).  A row-per-block mapping idles a third of the threads on 513-node rows.
   const int nzr = gf.nzl + 2 * ghost;
-  const long long rows = (long long)gf.nn[1] * nzr;
-  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
-       row += (long long)gridDim.x * blockDim.y) {
-    const int iy = (int)(row % gf.nn[1]);
-    const int lz = (int)(row / gf.nn[1]) - ghost;
+  const unsigned npair = (unsigned)(gf.nn[0] + 1) / 2;
+  const long long total = (long long)gf.nn[1] * nzr * npair;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const unsigned row = (unsigned)(t / npair);
+    const int k = (int)(t - (long long)row * npair);
+    const int iy = (int)(row % (unsigned)gf.nn[1]);
+    const int lz = (int)(row / (unsigned)gf.nn[1]) - ghost;
     const int gz = lz + gf.z0;
     if (gz < 0 || gz > gf.nzg - 1) continue;   // ghost plane beyond the domain end
+    const int ix = 2 * k;
+    double bcv;
+    const bool f0 = !bc_node(gf, bcf, ix, iy, gz, &bcv);
+    const bool f1 = ix + 1 < gf.nn[0] && !bc_node(gf, bcf, ix + 1, iy, gz, &bcv);
+    if (!f0 && !f1) continue;
     const long long fbase = (long long)gf.PX * iy + gf.plane * lz;
     const int py = gf.nc[1] > 0 ? (iy & 1) : 0;
     const int pz = gf.nc[2] > 0 ? (gz & 1) : 0;
     const int cy = gf.nc[1] > 0 ? (iy - py) / 2 : 0;
     const int clz = (gf.nc[2] > 0 ? (gz - pz) / 2 : 0) - gc.z0;
-    const long long cbase = (long long)gc.PX * cy + gc.plane * clz;
+    const long long lo = (long long)gc.PX * cy + gc.plane * clz + k;
     const long long cpy = (long long)gc.PX * py + gc.plane * pz;
-    for (int ix = threadIdx.x; ix < gf.nn[0]; ix += blockDim.x) {
-      double bcv;
-      if (bc_node(gf, bcf, ix, iy, gz, &bcv)) continue;
-      const int px = ix & 1;
-      const long long lo = cbase + (ix - px) / 2;
-      const long long hi = lo + px + cpy;
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        const double* cp = xc + i * gc.comp_stride;
-        xf[fbase + ix + i * gf.comp_stride] += 0.5 * (cp[lo] + cp[hi]);
-      }
+    for (int i = 0; i < NC; ++i) {
+      const double* cp = xc + i * gc.comp_stride;
+      double2* fp = reinterpret_cast<double2*>(xf + fbase + ix + i * gf.comp_stride);
+      double2 v = *fp;
+      const double c0 = cp[lo];
+      if (f0) v.x += 0.5 * (c0 + cp[lo + cpy]);
+      if (f1) v.y += 0.5 * (c0 + cp[lo + 1 + cpy]);
+      *fp = v;
     }
   }
 }
 
 int launch_prolong_add(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcf, int ncomp, const double* xc,
                        double* xf, int ghost) {
-  RowLaunch rl = row_launch(c, gf);
-  DISPATCH_NC(ncomp, (k_prolong_add<NC><<<rl.grid, rl.block, 0, c->stream>>>(gf, gc, bcf, xc, xf, ghost)));
+  const long long total = (long long)gf.nn[1] * (gf.nzl + 2 * ghost) * ((gf.nn[0] + 1) / 2);
+  if (gf.nn[1] * (long long)(gf.nzl + 2 * ghost) >= (1LL << 32)) PDE_FAIL("prolongation: too many rows");
+  const int blocks = flat_blocks(c, total, 256);
+  DISPATCH_NC(ncomp, (k_prolong_add<NC><<<blocks, 256, 0, c->stream>>>(gf, gc, bcf, xc, xf, ghost)));
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
