@@ -68,6 +68,14 @@ __device__ __forceinline__ long long kOffDdev(int k, int PX, long long plane) {
   return D[k][0] + (long long)PX * D[k][1] + plane * D[k][2];
 }
 
+// component `ax` of Kuhn-stencil offset k (folds to a constant after unrolling)
+__device__ __forceinline__ int kOffDcomp(int k, int ax) {
+  constexpr int D[PDE_NOFF][3] = {{0, 0, 0},  {1, 0, 0},  {-1, 0, 0},  {0, 1, 0},  {0, -1, 0},
+                                  {0, 0, 1},  {0, 0, -1}, {1, 1, 0},   {-1, -1, 0}, {1, 0, 1},
+                                  {-1, 0, -1}, {0, 1, 1}, {0, -1, -1}, {1, 1, 1},   {-1, -1, -1}};
+  return D[k][ax];
+}
+
 // ----------------------------------------------------------------------------------------------
 // deterministic two-stage reduction: per-block partials, last block sums them in fixed order
 // ----------------------------------------------------------------------------------------------

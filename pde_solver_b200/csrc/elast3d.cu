@@ -57,11 +57,13 @@ struct EG {
   static_assert((TILE * 8) % 128 == 0, "TMA destinations must stay 128-byte aligned");
 };
 
-enum { EM_APPLY = 0, EM_RESID = 1, EM_CHEBY = 2 };
+enum { EM_APPLY = 0, EM_RESID = 1, EM_CHEBY = 2, EM_FIRST2 = 3 };
 
 struct ECoef {
   double k0[3], kx[3], ky[3], kz[3];   // K^{aa}: centre, +-x, +-y, +-z
-  double uxy, uxz, uyz, uxy2;          // coupling units; uxy2 = 2 uxy
+  // coupling units, indexed by the INPUT component B they multiply (all equal in B for the plain operator; the fused
+  // first-two-sweeps mode folds the column scaling s0 / diag[B] of x1 = s0 D^-1 b into them); uxy2 = 2 uxy
+  double uxy[3], uxz[3], uyz[3], uxy2[3];
 };
 struct EArgs {
   double* y;
@@ -103,44 +105,44 @@ __device__ __forceinline__ void e_contrib(const ECoef& C, const double (&V)[YS +
     a0[j][B] = fma(C.k0[B], f0, fma(C.kx[B], Sx, fma(C.ky[B], Sy, a0[j][B])));
     const double M = fma(-2.0, f0, (Sx + Sy) - Sd);           // xy pattern / 2
     if (B == 0) {
-      a0[j][1] = fma(C.uxy2, M, a0[j][1]);
-      a0[j][2] = fma(C.uxz, fma(3.0, fma(-2.0, f0, Sx), -M), a0[j][2]);
+      a0[j][1] = fma(C.uxy2[B], M, a0[j][1]);
+      a0[j][2] = fma(C.uxz[B], fma(3.0, fma(-2.0, f0, Sx), -M), a0[j][2]);
     } else if (B == 1) {
-      a0[j][0] = fma(C.uxy2, M, a0[j][0]);
-      a0[j][2] = fma(C.uyz, fma(3.0, fma(-2.0, f0, Sy), -M), a0[j][2]);
+      a0[j][0] = fma(C.uxy2[B], M, a0[j][0]);
+      a0[j][2] = fma(C.uyz[B], fma(3.0, fma(-2.0, f0, Sy), -M), a0[j][2]);
     } else {
-      a0[j][0] = fma(C.uxz, fma(3.0, fma(-2.0, f0, Sx), -M), a0[j][0]);
-      a0[j][1] = fma(C.uyz, fma(3.0, fma(-2.0, f0, Sy), -M), a0[j][1]);
+      a0[j][0] = fma(C.uxz[B], fma(3.0, fma(-2.0, f0, Sx), -M), a0[j][0]);
+      a0[j][1] = fma(C.uyz[B], fma(3.0, fma(-2.0, f0, Sy), -M), a0[j][1]);
     }
     // dz = +1: g0 = V[r][1], gx = V[r][2], gy = V[r+1][1], gd = V[r+1][2]
     aP[j][B] = fma(C.kz[B], f0, aP[j][B]);
     if (B == 0) {
-      aP[j][1] = fma(C.uxy, P[r + 1] - P[r], aP[j][1]);
-      aP[j][2] = fma(C.uxz, fma(2.0, P[r], P[r + 1]), aP[j][2]);
+      aP[j][1] = fma(C.uxy[B], P[r + 1] - P[r], aP[j][1]);
+      aP[j][2] = fma(C.uxz[B], fma(2.0, P[r], P[r + 1]), aP[j][2]);
     } else if (B == 1) {
       const double R1 = V[r][1] - V[r + 1][1], R2 = V[r][2] - V[r + 1][2];
-      aP[j][0] = fma(C.uxy, R2 - R1, aP[j][0]);
-      aP[j][2] = fma(C.uyz, fma(2.0, R1, R2), aP[j][2]);
+      aP[j][0] = fma(C.uxy[B], R2 - R1, aP[j][0]);
+      aP[j][2] = fma(C.uyz[B], fma(2.0, R1, R2), aP[j][2]);
     } else {
       const double Exz = fma(2.0, P[r], P[r + 1]);
-      aP[j][0] = fma(C.uxz, Exz, aP[j][0]);
-      aP[j][1] = fma(C.uyz, fma(3.0, V[r][2] - V[r + 1][1], Exz), aP[j][1]);
+      aP[j][0] = fma(C.uxz[B], Exz, aP[j][0]);
+      aP[j][1] = fma(C.uyz[B], fma(3.0, V[r][2] - V[r + 1][1], Exz), aP[j][1]);
     }
     // dz = -1: g0 = V[r][1], gx = V[r][0], gy = V[r-1][1], gd = V[r-1][0]
     if (B == 0) {
       aM[j][0] = C.kz[0] * f0;
-      aM[j][1] = C.uxy * (Q[r - 1] - Q[r]);
-      aM[j][2] = C.uxz * fma(2.0, Q[r], Q[r - 1]);
+      aM[j][1] = C.uxy[B] * (Q[r - 1] - Q[r]);
+      aM[j][2] = C.uxz[B] * fma(2.0, Q[r], Q[r - 1]);
     } else if (B == 1) {
       const double R1 = V[r][1] - V[r - 1][1], R2 = V[r][0] - V[r - 1][0];
       aM[j][1] = fma(C.kz[1], f0, aM[j][1]);
-      aM[j][0] = fma(C.uxy, R2 - R1, aM[j][0]);
-      aM[j][2] = fma(C.uyz, fma(2.0, R1, R2), aM[j][2]);
+      aM[j][0] = fma(C.uxy[B], R2 - R1, aM[j][0]);
+      aM[j][2] = fma(C.uyz[B], fma(2.0, R1, R2), aM[j][2]);
     } else {
       const double Exz = fma(2.0, Q[r], Q[r - 1]);
       aM[j][2] = fma(C.kz[2], f0, aM[j][2]);
-      aM[j][0] = fma(C.uxz, Exz, aM[j][0]);
-      aM[j][1] = fma(C.uyz, fma(3.0, V[r][0] - V[r - 1][1], Exz), aM[j][1]);
+      aM[j][0] = fma(C.uxz[B], Exz, aM[j][0]);
+      aM[j][1] = fma(C.uyz[B], fma(3.0, V[r][0] - V[r - 1][1], Exz), aM[j][1]);
     }
   }
 }
@@ -149,6 +151,10 @@ __device__ __forceinline__ void e_contrib(const ECoef& C, const double (&V)[YS +
 //       EM_RESID  y = m (ascale A x + bscale b)       reductions x.y, y.y
 //       EM_CHEBY  y = x + m (c1 d + c2 D^-1 (b - A x)) reduction b.y ; d = x - x_prev (PREV: x_prev is loaded),
 //                 x (prev_mode 2: the previous iterate is zero) or 0 (restart)
+//       EM_FIRST2 the first TWO sweeps from a zero guess in one pass: the input field is the right-hand side b, the
+//                 coefficients arrive with their columns scaled by s0 / diag (so the stencil yields A x1, x1 = s0 D^-1 b),
+//                 y = (1 + c1) x1 + c2 D^-1 (b - A x1).  Valid where every neighbour carries the interior diagonal:
+//                 rows on AND next to natural faces are left to k_face_rows (two layers), which knows the class diagonals
 // TOUT: the output plane is staged in shared memory and written by a TMA store (which clips at the domain boundary);
 //       otherwise every thread stores its own values (no shared-memory traffic, but address arithmetic and predicates).
 template <int MODE, bool PREV, int YS, bool TOUT>
@@ -158,8 +164,9 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
           const __grid_constant__ ECoef C, const __grid_constant__ EArgs a, const __grid_constant__ EGeom ge,
           ReduceBuf red, double* red_out, const double* face_part, int nface_part) {
   using G = EG<YS>;
-  constexpr bool HAS_B = MODE != EM_APPLY;
+  constexpr bool HAS_B = MODE == EM_RESID || MODE == EM_CHEBY;
   constexpr bool CHEBY = MODE == EM_CHEBY;
+  constexpr bool FIRST2 = MODE == EM_FIRST2;
   constexpr int NAUX = (HAS_B ? 1 : 0) + (PREV ? 1 : 0);
   constexpr int STAGE_ELEMS = G::XSTAGE + NAUX * G::TILE;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -226,7 +233,11 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
       const bool in = xin && iy < ge.nn1;
       if (in) okb |= 1u << j;
       if (in && !d) fre |= 1u << j;
-      if (in && !d && (xe0 || xe1 || ye0 || ye1)) slow |= 1u << j;
+      bool sl = xe0 || xe1 || ye0 || ye1;
+      // fused first sweeps: also the layer next to a NATURAL x / y face (its neighbours carry another diagonal)
+      if (FIRST2) sl = sl || (ix == 1 && !ge.on[0]) || (ix == ge.nn0 - 2 && !ge.on[1]) || (iy == 1 && !ge.on[2]) ||
+                       (iy == ge.nn1 - 2 && !ge.on[3]);
+      if (in && !d && sl) slow |= 1u << j;
     }
   }
   const unsigned fast = fre & ~slow;            // rows this kernel computes on a generic plane
@@ -276,7 +287,8 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
     if (FIN) {
       // plane type: generic / Dirichlet (or beyond the domain) / natural z face
       const int gz = zout + ge.z0;
-      const bool zface = gz == 0 || gz == ge.nzg - 1;
+      const bool zface = gz == 0 || gz == ge.nzg - 1 ||
+                         (FIRST2 && ((gz == 1 && !ge.on[4]) || (gz == ge.nzg - 2 && !ge.on[5])));
       const bool zface_dir = (gz == 0 && ge.on[4]) || (gz == ge.nzg - 1 && ge.on[5]);
       const bool zdir = gz < 0 || gz > ge.nzg - 1 || (zface_dir && !z_excl);
       const unsigned comp = (zdir || zface) ? 0u : fast;             // rows computed here
@@ -306,6 +318,9 @@ k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUten
             // TMA output, PREV: the output may alias x_prev, which k_face_rows still reads on its rows: hand it back
             if (TOUT && PREV) yv = k ? xo - dprev : yv;
             red_xy = fma(m ? Bv : 0.0, yv, red_xy);
+          } else if (FIRST2) {
+            // xo is the right-hand side here; A = A x1 (scaled coefficients)
+            yv = m ? fma(a.bB[q], xo, a.c2d[q] * (xo - A)) : 0.0;      // bB = (1 + c1) s0 / diag
           } else {
             const double Bt = HAS_B ? a.bscale * bt[q * G::TCOMP + j * E_TX] : a.bB[q];
             yv = m ? fma(a.ascale, A, Bt) : 0.0;
@@ -363,14 +378,16 @@ bool extract_coef(const OpDev& op, ECoef* C) {
   for (int q = 0; q < PDE_NOFF * 9; ++q) mx = fmax(mx, fabs(h[q]));
   if (!(mx > 0)) return false;
   for (int c = 0; c < 3; ++c) { C->k0[c] = H(0, c, c); C->kx[c] = H(1, c, c); C->ky[c] = H(3, c, c); C->kz[c] = H(5, c, c); }
-  C->uxy = -H(13, 0, 1);
-  C->uxz = -H(13, 0, 2);
-  C->uyz = -H(13, 1, 2);
-  C->uxy2 = 2.0 * C->uxy;
+  for (int c = 0; c < 3; ++c) {
+    C->uxy[c] = -H(13, 0, 1);
+    C->uxz[c] = -H(13, 0, 2);
+    C->uyz[c] = -H(13, 1, 2);
+    C->uxy2[c] = 2.0 * C->uxy[c];
+  }
   // offsets: 0 centre, 1/2 +-x, 3/4 +-y, 5/6 +-z, 7/8 +-(x+y), 9/10 +-(x+z), 11/12 +-(y+z), 13/14 +-(x+y+z)
   static const int pat[3][8] = {{-4, 2, 2, -1, -2, 1, 1, -1}, {-4, 2, -1, 2, 1, -2, 1, -1}, {-4, -1, 2, 2, 1, 1, -2, -1}};
   const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
-  const double un[3] = {C->uxy, C->uxz, C->uyz};
+  const double un[3] = {C->uxy[0], C->uxz[0], C->uyz[0]};
   const double tol = 1e-12 * mx;
   for (int k = 0; k < PDE_NOFF; ++k) {
     const int grp = k == 0 ? 0 : (k + 1) / 2;
@@ -397,7 +414,7 @@ const ETune& etune() {
 template <int MODE, bool PREV, int YS, bool TOUT>
 int launch_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, const ECoef& C) {
   using G = EG<YS>;
-  constexpr int NAUX = (MODE != EM_APPLY ? 1 : 0) + (PREV ? 1 : 0);
+  constexpr int NAUX = ((MODE == EM_RESID || MODE == EM_CHEBY) ? 1 : 0) + (PREV ? 1 : 0);
   EGeom ge;
   ge.nn0 = g.nn[0]; ge.nn1 = g.nn[1]; ge.nzl = g.nzl; ge.z0 = g.z0; ge.nzg = g.nzg;
   for (int i = 0; i < 6; ++i) ge.on[i] = bc.on[i];
@@ -424,14 +441,22 @@ int launch_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const 
   CUtensorMap tmx, tmb, tmp, tmy;
   PDE_OK(field_tensor_map(a.x, g, 3, E_BX, G::BY, &tmx));
   tmb = tmp = tmy = tmx;   // unused maps still have to be valid kernel parameters
-  if (MODE != EM_APPLY) PDE_OK(field_tensor_map(a.b, g, 3, E_TX, G::TY, &tmb));
+  if (MODE == EM_RESID || MODE == EM_CHEBY) PDE_OK(field_tensor_map(a.b, g, 3, E_TX, G::TY, &tmb));
   if (PREV) PDE_OK(field_tensor_map(a.xprev, g, 3, E_TX, G::TY, &tmp));
   if (TOUT && a.y) PDE_OK(field_tensor_map(a.y, g, 3, E_TX, G::TY, &tmy));
   EArgs ea;
   ea.y = a.y;
+  ECoef Cs = C;
   for (int i = 0; i < 3; ++i) {
     ea.bB[i] = a.bscale * a.bconst[i] * op.h_load_int;
     ea.c2d[i] = a.c2 * op.h_dinv_int[i];
+    if (MODE == EM_FIRST2) {
+      // x1 = s0 D^-1 b: fold the column scaling into the coefficients, y = (1 + c1) x1 + c2 D^-1 (b - A x1)
+      const double sg = a.s0 * op.h_dinv_int[i];
+      ea.bB[i] = (1.0 + a.c1) * sg;
+      Cs.k0[i] *= sg; Cs.kx[i] *= sg; Cs.ky[i] *= sg; Cs.kz[i] *= sg;
+      Cs.uxy[i] *= sg; Cs.uxz[i] *= sg; Cs.uyz[i] *= sg; Cs.uxy2[i] *= sg;
+    }
   }
   ea.ascale = a.ascale; ea.bscale = a.bscale; ea.c1 = a.c1;
   ea.prev_mode = a.prev_mode;
@@ -444,7 +469,7 @@ int launch_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const 
   // the TMA output path this kernel writes whole tiles, so the face rows have to be written after it.
   int nfp = 0;
   if (!TOUT && !op.uniform_diag) PDE_OK(launch_face_rows(c, g, bc, op, a, &nfp));
-  kern<<<(unsigned)items, E_NT, smem, c->stream>>>(tmx, tmb, tmp, tmy, C, ea, ge, c->red, out, c->face_partials, nfp);
+  kern<<<(unsigned)items, E_NT, smem, c->stream>>>(tmx, tmb, tmp, tmy, Cs, ea, ge, c->red, out, c->face_partials, nfp);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   if (TOUT && !op.uniform_diag) PDE_OK(launch_face_rows(c, g, bc, op, a));
@@ -453,6 +478,7 @@ int launch_t(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const 
 
 template <int YS, bool TOUT>
 int launch_mode(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, const ECoef& C) {
+  if (a.cheby == 2) return launch_t<EM_FIRST2, false, YS, TOUT>(c, g, bc, op, a, C);
   if (a.cheby)
     return a.prev_mode == 1 ? launch_t<EM_CHEBY, true, YS, TOUT>(c, g, bc, op, a, C)
                             : launch_t<EM_CHEBY, false, YS, TOUT>(c, g, bc, op, a, C);
@@ -467,7 +493,8 @@ int launch_elast3d(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, 
   *handled = false;
   static const int off = env_int("PDE_B200_NO_ELAST3D", 0);
   if (off || op.ncomp != 3 || g.dim != 3 || g.nk != PDE_NOFF) return 0;
-  if (a.ghost_out || a.cheby == 2 || (a.cheby && (a.prev_mode == 3 || !a.b))) return 0;
+  if (a.ghost_out || (a.cheby == 1 && (a.prev_mode == 3 || !a.b))) return 0;
+  if (a.cheby == 2 && (bc.side_excl || a.reduce_slot_xy >= 0 || !env_int("PDE_B200_E_FIRST2", 1))) return 0;
   if (a.cheby && a.prev_mode == 1 && !a.xprev) return 0;
   ECoef C;
   if (!extract_coef(op, &C)) return 0;
@@ -483,4 +510,15 @@ int launch_elast3d(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, 
   if (ys == 4) E_DISPATCH(4);
   E_DISPATCH(2);
 #undef E_DISPATCH
+}
+
+// can the smoother use the fused first-two-sweeps mode on this level?  (the caller must know before it decides between
+// one fused launch and cheby_first + sweep)
+bool elast3d_first2_ok(const Grid& g, const BcDev& bc, const OpDev& op) {
+  static const int off = env_int("PDE_B200_NO_ELAST3D", 0);
+  static const int on = env_int("PDE_B200_E_FIRST2", 1);
+  if (off || !on || op.ncomp != 3 || g.dim != 3 || g.nk != PDE_NOFF || bc.side_excl) return false;
+  if (!sweep_applicable(g, 3)) return false;
+  ECoef C;
+  return extract_coef(op, &C);
 }

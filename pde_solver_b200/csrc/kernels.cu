@@ -267,10 +267,10 @@ k_cg_pupdate(const __grid_constant__ Grid g, const double* __restrict__ dinv, do
 // ----------------------------------------------------------------------------------------------
 struct FaceSet {
   int nface;
-  int axis[6], fixed[6];          // fixed axis and its index (z: LOCAL plane)
-  int lo[6][2], cnt[6][2];        // the two varying axes (ascending axis order): start and count
-  int tiles0[6];                  // tiles of FACE_TU nodes along the first varying axis
-  int tstart[7];                  // prefix sums of the tile counts: one CTA per FACE_TU x FACE_TV tile
+  int axis[12], fixed[12];        // fixed axis and its index (z: LOCAL plane); up to two layers per face
+  int lo[12][2], cnt[12][2];      // the two varying axes (ascending axis order): start and count
+  int tiles0[12];                 // tiles of FACE_TU nodes along the first varying axis
+  int tstart[13];                 // prefix sums of the tile counts: one CTA per FACE_TU x FACE_TV tile
 };
 #define FACE_TU 32
 #define FACE_TV 8
@@ -297,12 +297,13 @@ k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, co
   constexpr int ROWP = (ROW + 1) / 2 * 2;   // rows stay 16-byte aligned
   __shared__ __align__(16) double s_coef[FULL ? PDE_NCLASS * ROWP : 2];
   __shared__ unsigned s_mask, s_nz[PDE_NCLASS];
+  __shared__ double s_dinv[PDE_NCLASS * NC];
   double acc_xy = 0.0, acc_yy = 0.0;
   {
     const int tile = blockIdx.x;
     int f = 0;
 #pragma unroll
-    for (int q = 1; q < 6; ++q) f += (q < fs.nface && tile >= fs.tstart[q]) ? 1 : 0;
+    for (int q = 1; q < 12; ++q) f += (q < fs.nface && tile >= fs.tstart[q]) ? 1 : 0;
     const int tl = tile - fs.tstart[f];
     const int tv = tl / fs.tiles0[f], tu = tl - tv * fs.tiles0[f];
     const int ul = tu * FACE_TU + (threadIdx.x & (FACE_TU - 1)), vl = tv * FACE_TV + (threadIdx.x / FACE_TU);
@@ -341,6 +342,8 @@ k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, co
       pv[i] = (CHEBY && a.prev_mode == 1) ? (a.xprev + i * g.comp_stride)[idxl] : 0.0;
     }
     if (FULL) {
+      if (CHEBY && a.first2)
+        for (int e = threadIdx.x; e < PDE_NCLASS * NC; e += blockDim.x) s_dinv[e] = __ldg(dinv + e);
       if (threadIdx.x < PDE_NCLASS) s_nz[threadIdx.x] = 0u;
       if (threadIdx.x == 0) s_mask = 0u;
       __syncthreads();
@@ -361,6 +364,18 @@ k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, co
       double acc[NC];
 #pragma unroll
       for (int i = 0; i < NC; ++i) acc[i] = 0.0;
+      if (FULL && CHEBY && a.first2) {
+        // fused first two sweeps: the loaded field is the right-hand side b; x1 = s0 D^-1 b with the class diagonal of
+        // EVERY neighbour (that is why the layer next to a natural face is computed here too)
+#pragma unroll
+        for (int k = 0; k < PDE_NOFF; ++k) {
+          const int jx = ix + kOffDcomp(k, 0), jy = iy + kOffDcomp(k, 1), jz = lz + g.z0 + kOffDcomp(k, 2);
+          const bool in = jx >= 0 && jx < g.nn[0] && jy >= 0 && jy < g.nn[1] && jz >= 0 && jz < g.nzg;
+          const int ck = in ? node_class(g, jx, jy, jz) : 13;
+#pragma unroll
+          for (int j = 0; j < NC; ++j) xv[k][j] *= a.s0 * s_dinv[ck * NC + j];
+        }
+      }
       if (FULL) {
         const double* cf = s_coef + cls * ROWP;
         const unsigned nz = s_nz[cls];
@@ -390,7 +405,11 @@ k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, co
 #pragma unroll
       for (int i = 0; i < NC; ++i) {
         const double B = a.b ? bv[i] : a.bconst[i] * ld;
-        if (CHEBY) {
+        if (CHEBY && a.first2) {
+          // xo = b (raw), xv[0] = x1 of this node: y = (1 + c1) x1 + c2 D^-1 (b - A x1)
+          const double yv = fma(1.0 + a.c1, xv[0][i], a.c2 * s_dinv[cls * NC + i] * (xo[i] - acc[i]));
+          (a.y + i * g.comp_stride)[idxl] = yv;
+        } else if (CHEBY) {
           const double dprev = a.prev_mode == 1 ? xo[i] - pv[i] : (a.prev_mode == 2 ? xo[i] : 0.0);
           const double dn = a.c1 * dprev + a.c2 * __ldg(dinv + cls * NC + i) * (B - acc[i]);
           const double yv = xo[i] + dn;
@@ -435,13 +454,17 @@ k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, co
 
 int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, int* defer_blocks) {
   if (defer_blocks) *defer_blocks = 0;
-  if (a.cheby == 2) PDE_FAIL("fused first sweeps need a uniform diagonal (no natural faces)");
+  // fused first sweeps (cheby == 2): x1 = s0 D^-1 b needs the class diagonal of every neighbour, so the layer NEXT to a
+  // natural face is computed here as well (two layers); only the 3-D kernel with the cached class table implements it
+  const int layers = a.cheby == 2 ? 2 : 1;
+  if (layers == 2 && (bc.side_excl || g.dim != 3 || a.reduce_slot_xy >= 0))
+    PDE_FAIL("fused first sweeps on natural faces need a 3-D operator without the other_faces rule and no reduction");
   FaceSet fs;
   memset(&fs, 0, sizeof(fs));
   long long ntiles = 0;
   const int n0 = g.nn[0], n1 = g.nn[1];
   auto add = [&](int axis, int fixed, int lo0, int c0, int lo1, int c1) {
-    if (c0 <= 0 || c1 <= 0) return;
+    if (c0 <= 0 || c1 <= 0 || fs.nface >= 12) return;
     const int f = fs.nface++;
     fs.axis[f] = axis; fs.fixed[f] = fixed;
     fs.lo[f][0] = lo0; fs.cnt[f][0] = c0; fs.lo[f][1] = lo1; fs.cnt[f][1] = c1;
@@ -452,18 +475,26 @@ int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op
   // a face whose Dirichlet flag is set contributes no free rows, except that the reference's "other_faces"
   // rule (side_excl) leaves the x-end columns of side faces free: keep such faces listed
   const bool keep_all = bc.side_excl != 0;
-  if (g.nc[0] > 0) {
-    if (!bc.on[0] || keep_all) add(0, 0, 0, n1, 0, g.nzl);
-    if (!bc.on[1] || keep_all) add(0, n0 - 1, 0, n1, 0, g.nzl);
-  }
-  if (g.nc[1] > 0 && n0 > 2) {
-    if (!bc.on[2] || keep_all) add(1, 0, 1, n0 - 2, 0, g.nzl);
-    if (!bc.on[3] || keep_all) add(1, n1 - 1, 1, n0 - 2, 0, g.nzl);
-  }
-  if (g.nc[2] > 0 && n0 > 2 && (n1 > 2 || g.nc[1] == 0)) {
-    const int ylo = g.nc[1] > 0 ? 1 : 0, ycnt = g.nc[1] > 0 ? n1 - 2 : 1;
-    if (g.z0 == 0 && (!bc.on[4] || keep_all)) add(2, 0, 1, n0 - 2, ylo, ycnt);
-    if (g.z0 + g.nzl == g.nzg && (!bc.on[5] || keep_all)) add(2, g.nzl - 1, 1, n0 - 2, ylo, ycnt);
+  const bool nat[6] = {!bc.on[0] || keep_all, !bc.on[1] || keep_all, !bc.on[2] || keep_all,
+                       !bc.on[3] || keep_all, !bc.on[4] || keep_all, !bc.on[5] || keep_all};
+  // nodes already taken by the x layers (y, z sets) and by the y layers (z sets)
+  const int xl = (layers == 2 && nat[0]) ? 2 : 1, xh = (layers == 2 && nat[1]) ? n0 - 3 : n0 - 2;
+  const int yl = g.nc[1] > 0 ? ((layers == 2 && nat[2]) ? 2 : 1) : 0;
+  const int yh = g.nc[1] > 0 ? ((layers == 2 && nat[3]) ? n1 - 3 : n1 - 2) : 0;
+  for (int ly = 0; ly < layers; ++ly) {
+    if (g.nc[0] > 0 && n0 > 2 * ly) {
+      if (nat[0]) add(0, ly, 0, n1, 0, g.nzl);
+      if (nat[1]) add(0, n0 - 1 - ly, 0, n1, 0, g.nzl);
+    }
+    if (g.nc[1] > 0 && n1 > 2 * ly) {
+      if (nat[2]) add(1, ly, xl, xh - xl + 1, 0, g.nzl);
+      if (nat[3]) add(1, n1 - 1 - ly, xl, xh - xl + 1, 0, g.nzl);
+    }
+    if (g.nc[2] > 0 && (n1 > 2 || g.nc[1] == 0)) {
+      const int zlo = ly - g.z0, zhi = g.nzg - 1 - ly - g.z0;          // local planes of the two layers
+      if (nat[4] && zlo >= 0 && zlo < g.nzl) add(2, zlo, xl, xh - xl + 1, yl, yh - yl + 1);
+      if (nat[5] && zhi >= 0 && zhi < g.nzl && zhi != zlo) add(2, zhi, xl, xh - xl + 1, yl, yh - yl + 1);
+    }
   }
   if (ntiles == 0) return 0;
   if (ntiles > RED_MAX_BLOCKS) PDE_FAIL("face grid exceeds the reduction buffer");
@@ -472,12 +503,13 @@ int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op
   for (int i = 0; i < 3; ++i) sd.bconst[i] = a.bconst[i];
   sd.bscale = a.bscale; sd.ascale = a.ascale; sd.c1 = a.c1; sd.c2 = a.c2; sd.s0 = a.s0;
   sd.do_reduce = a.reduce_slot_xy >= 0;
-  sd.first2 = 0;
+  sd.first2 = a.cheby == 2;
   sd.defer = (defer_blocks && sd.do_reduce) ? c->face_partials : nullptr;
   const int blocks = (int)ntiles;
   if (sd.defer) *defer_blocks = blocks;
   bool full = g.dim == 3 && g.nk == PDE_NOFF && g.comp_stride * op.ncomp < (1LL << 31);
   for (int k = 0; full && k < PDE_NOFF; ++k) full = g.kidx[k] == k;
+  if (layers == 2 && !full) PDE_FAIL("fused first sweeps on natural faces: grid too large for the 3-D face kernel");
   double* out = sd.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
 #define FACE_LAUNCH(CH, FU)                                                                                      \
   DISPATCH_NC(op.ncomp, (k_face_rows<NC, CH, FU><<<blocks, FACE_NT, 0, c->stream>>>(g, bc, fs, op.coef, op.dinv, op.load, \

@@ -14,6 +14,7 @@ int launch_stencil_generic(pde_ctx* c, const Grid& g, const BcDev& bc, const OpD
 int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, bool* handled);
 int launch_heat_post2(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, double* y, double c2_0,
                       double c1_1, double c2_1, int dot_slot, bool* handled);
+bool elast3d_first2_ok(const Grid& g, const BcDev& bc, const OpDev& op);
 int launch_heat_resid_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const OpDev& op, const double* x, const double* b,
                                double* bcoarse, bool* handled);
 
@@ -432,7 +433,9 @@ static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double*
   int prev_mode = 0;   // how sweep k rebuilds d_{k-1} = x_k - x_{k-1}
   double s0 = 0;
   if (dot_done) *dot_done = false;
-  if (zero_guess && sweeps >= 2 && L.op.dev.uniform_diag) {
+  // vector operators with natural faces: k_elast3d + the two-layer face kernel (no fused dot product there)
+  const bool e_first2 = !L.op.dev.uniform_diag && dot_slot < 0 && elast3d_first2_ok(L.op.g, L.op.bc, L.op.dev);
+  if (zero_guess && sweeps >= 2 && (L.op.dev.uniform_diag || e_first2)) {
     // sweeps 0 and 1 in one pass over the data: x1 = s0 D^-1 b never touches memory
     StencilArgs a;
     double c1;
