@@ -46,6 +46,7 @@ extern "C" int pde_ctx_destroy(pde_ctx* c) {
   cudaFree(c->red.partials);
   cudaFree(c->red.counter);
   cudaFree(c->face_partials);
+  if (c->scratch) cudaFree(c->scratch);
   cudaFree(c->scal);
   cudaFreeHost(c->h_scal);
   cudaEventDestroy(c->ev0);

@@ -21,6 +21,8 @@ struct pde_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll = nullptr;
   ReduceBuf red{};
+  void* scratch = nullptr;           // grow-only device scratch (cell sums of the von Mises load vector)
+  size_t scratch_bytes = 0;
   double* face_partials = nullptr;   // [RED_MAX_BLOCKS][RED_MAX_VALS]: block sums of a deferred face-row kernel
   double* scal = nullptr;     // device [S_NSLOTS]
   double* h_scal = nullptr;   // pinned, mapped host mirror [S_NSLOTS]

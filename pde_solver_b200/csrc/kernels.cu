@@ -1159,8 +1159,161 @@ k_cell_rhs(const __grid_constant__ Grid g, const __grid_constant__ SimplexGeom s
   }
 }
 
+// ---- 3-D von Mises load vector in two passes ---------------------------------------------------------------------
+// k_cell_rhs evaluates the 24 simplices around every node (each simplex four times over, with table-driven gradients):
+// 29.6 ms at config 5, 60x off its traffic.  The 3-D path computes every Kuhn simplex ONCE per cell (k_cell_vm: three
+// edge differences per component give the displacement gradient of the path simplex 0 -> e_a -> e_a+e_b -> (1,1,1)) and
+// leaves, per cell, the sum of the values of the simplices that contain each of its corners (7 planes of doubles, SoA;
+// corners 0 and 7 are in all six); k_cell_gather then adds the (up to) eight cell-corner sums of a node in fixed order.
+__device__ __forceinline__ double vm_value(const double (&gu)[3][3], int mode, double lam, double mu) {
+  double eps[3][3];
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) eps[i][j] = 0.5 * (gu[i][j] + gu[j][i]);
+    tr += eps[i][i];
+  }
+  double ss = 0.0;
+  if (mode == 1) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double dv = eps[i][j] - (i == j ? (1.0 / 3.0) * tr : 0.0);
+        ss = fma(dv, dv, ss);
+      }
+    return sqrt(2.0 / 3.0 * ss);
+  }
+  double trs = 0.0, sig[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sig[i][j] = 2.0 * mu * eps[i][j] + (i == j ? lam * tr : 0.0);
+    trs += sig[i][i];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double dv = sig[i][j] - (i == j ? (1.0 / 3.0) * trs : 0.0);
+      ss = fma(dv, dv, ss);
+    }
+  return sqrt(3.0 / 2.0 * ss);
+}
+
+// cells: x fastest, then y, then local cell layer lz - lzmin (the layer below local plane 0 uses the lower halo plane)
+__global__ void __launch_bounds__(256)
+k_cell_vm(const __grid_constant__ Grid g, const double* __restrict__ u, double* __restrict__ S, long long ncells, int lzmin,
+          int mode, double lam, double mu) {
+  const double ih[3] = {1.0 / g.h[0], 1.0 / g.h[1], 1.0 / g.h[2]};
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < ncells; t += (long long)gridDim.x * blockDim.x) {
+    const int cx = (int)(t % g.nc[0]);
+    const long long r = t / g.nc[0];
+    const int cy = (int)(r % g.nc[1]);
+    const int lz = (int)(r / g.nc[1]) + lzmin;
+    const long long base = (long long)g.PX * cy + g.plane * lz + cx;
+    double uc[8][3];   // corner o = ox + 2 oy + 4 oz
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        uc[o][i] = u[base + (o & 1) + (long long)g.PX * ((o >> 1) & 1) + g.plane * ((o >> 2) & 1) + i * g.comp_stride];
+    double Sv[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) Sv[o] = 0.0;
+    // the six Kuhn simplices: path 0 -> e_a -> e_a + e_b -> 7 for the permutations (a, b, c)
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      constexpr int P[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+      const int a = P[p][0], b = P[p][1], cc = P[p][2];
+      const int v1 = 1 << a, v2 = v1 | (1 << b);
+      double gu[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        gu[i][a] = (uc[v1][i] - uc[0][i]) * ih[a];
+        gu[i][b] = (uc[v2][i] - uc[v1][i]) * ih[b];
+        gu[i][cc] = (uc[7][i] - uc[v2][i]) * ih[cc];
+      }
+      const double val = vm_value(gu, mode, lam, mu);
+      Sv[0] += val; Sv[v1] += val; Sv[v2] += val;
+    }
+#pragma unroll
+    for (int o = 0; o < 7; ++o) S[(long long)o * ncells + t] = Sv[o];   // corner 7 = corner 0: every simplex has both
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_cell_gather(const __grid_constant__ Grid g, const double* __restrict__ S, double* __restrict__ rhs, long long ncells,
+              int lzmin, int lzmax, double w, int pa, int pb) {
+  // node planes [pa, pb); S holds the cell layers lzmin .. lzmax (layers outside the domain are simply not listed)
+  const long long nodes = (long long)g.nn[0] * g.nn[1] * (pb - pa);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nodes; t += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(t % g.nn[0]);
+    const long long r = t / g.nn[0];
+    const int iy = (int)(r % g.nn[1]);
+    const int lz = (int)(r / g.nn[1]) + pa;
+    double acc = 0.0;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int cx = ix - (o & 1), cy = iy - ((o >> 1) & 1), cz = lz - ((o >> 2) & 1);
+      if (cx < 0 || cx >= g.nc[0] || cy < 0 || cy >= g.nc[1] || cz < lzmin || cz > lzmax) continue;
+      const long long cell = cx + (long long)g.nc[0] * (cy + (long long)g.nc[1] * (cz - lzmin));
+      acc += S[(long long)(o == 7 ? 0 : o) * ncells + cell];
+    }
+    rhs[(long long)g.PX * iy + g.plane * lz + ix] = w * acc;
+  }
+}
+
+// is the simplex table the Kuhn split (every simplex a path 0 -> e_a -> e_a + e_b -> 7)?
+static bool kuhn_split(const SimplexGeom& sg) {
+  if (sg.nsimp != 6 || sg.nv != 4) return false;
+  unsigned seen = 0;
+  for (int t = 0; t < 6; ++t) {
+    unsigned set = 0;
+    for (int a = 0; a < 4; ++a) set |= 1u << sg.corner[t][a];
+    if (!(set & 1u) || !(set & 128u) || __builtin_popcount(set) != 4) return false;
+    int v1 = -1, v2 = -1;
+    for (int o = 1; o < 7; ++o)
+      if (set & (1u << o)) { if (__builtin_popcount((unsigned)o) == 1) v1 = o; else v2 = o; }
+    if (v1 < 0 || v2 < 0 || (v1 & v2) != v1) return false;
+    seen |= 1u << (v1 * 8 + v2) % 32;
+  }
+  return __builtin_popcount(seen) == 6;
+}
+
 int launch_cell_rhs(pde_ctx* c, const Grid& g, int ncomp, const SimplexGeom& sg, const double* u, double* rhs,
                     int mode, double lam, double mu, double Emod) {
+  static const int two_pass = getenv("PDE_B200_CELL_2PASS") ? atoi(getenv("PDE_B200_CELL_2PASS")) : 1;
+  if (two_pass && g.dim == 3 && ncomp == 3 && mode <= 1 && kuhn_split(sg) && g.nc[0] > 0 && g.nc[1] > 0 && g.nc[2] > 0) {
+    // chunks of node planes, so that the cell-sum scratch stays small and cached on the context (a 4.7 GB allocation per
+    // solve costs tens of milliseconds and, now and then, most of a second)
+    const int gl0 = g.z0 > 0 ? -1 : 0;                                   // first / last cell layer this rank can form
+    const int gl1 = (g.nzl - 1 > g.nzg - 2 - g.z0) ? g.nzg - 2 - g.z0 : g.nzl - 1;
+    const long long per_layer = (long long)g.nc[0] * g.nc[1];
+    int chunk = (int)((48LL << 20) / (per_layer > 0 ? per_layer : 1));   // about 48 M cells (2.7 GB / 7 planes -> 384 MB) at most
+    chunk = chunk < 2 ? 2 : (chunk > 32 ? 32 : chunk);
+    const size_t need = sizeof(double) * 7 * (size_t)per_layer * (chunk + 1);
+    if (c->scratch_bytes < need) {
+      if (c->scratch) { CUDA_OK(cudaStreamSynchronize(c->stream)); CUDA_OK(cudaFree(c->scratch)); c->scratch = nullptr; c->scratch_bytes = 0; }
+      CUDA_OK(cudaMalloc(&c->scratch, need));
+      c->scratch_bytes = need;
+    }
+    double* S = (double*)c->scratch;
+    for (int pa = 0; pa < g.nzl; pa += chunk) {
+      const int pb = pa + chunk < g.nzl ? pa + chunk : g.nzl;
+      const int lzmin = pa - 1 < gl0 ? gl0 : pa - 1;                     // node plane p touches the cell layers p-1 and p
+      const int lzmax = pb - 1 > gl1 ? gl1 : pb - 1;
+      const long long ncells = per_layer * (lzmax - lzmin + 1);
+      if (ncells > 0)
+        k_cell_vm<<<flat_blocks(c, ncells, 256), 256, 0, c->stream>>>(g, u, S, ncells, lzmin, mode, lam, mu);
+      k_cell_gather<<<flat_blocks(c, (long long)g.nn[0] * g.nn[1] * (pb - pa), 256), 256, 0, c->stream>>>(
+          g, S, rhs, ncells > 0 ? ncells : 1, lzmin, lzmax, sg.vol / 4.0, pa, pb);
+      c->launches += 2;
+    }
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   RowLaunch rl = row_launch(c, g);
   DISPATCH_NC(ncomp, (k_cell_rhs<NC><<<rl.grid, rl.block, 0, c->stream>>>(g, sg, u, rhs, mode, lam, mu, Emod)));
   c->launches++;
