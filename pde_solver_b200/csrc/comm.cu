@@ -194,7 +194,10 @@ k_halo_p2p(const __grid_constant__ HaloArgs a) {
     if (hi) wait_flag(a.my_flags + F_ARR1, a.seq, a.err);
   }
   __syncthreads();
-  for (int c = 0; c < a.ncomp; ++c) {
+  // a wait that timed out leaves stale inbox slots: do not move them into the ghost planes (the host fails at its next
+  // poll; nothing computed from them may reach an output that is fetched without one)
+  const bool dead = *(volatile int*)a.err != 0;
+  for (int c = 0; c < a.ncomp && !dead; ++c) {
     if (lo) {
       copy_d2<true>(reinterpret_cast<double2*>(a.ghost_lo + c * a.comp_stride),
                     reinterpret_cast<const double2*>(a.in_lo + c * a.n), n2, g0, gsz);

@@ -316,6 +316,13 @@ int dispatch(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const
 
 }  // namespace
 
+// does one of the fused post-smoothing kernels (k_heat_post2, or k_post2 of round 1) take this level?
+bool post2_applicable(const Grid& g, const OpDev& op) {
+  if (g.dim != 3 || g.nk != PDE_NOFF || op.ncomp != 1 || !op.uniform_diag) return false;
+  if (g.nn[0] < 32 || g.nn[1] < 8 || g.nzl < 8) return false;
+  return !env_int("PDE_B200_NO_HEAT2", 0) || !env_int("PDE_B200_NO_POST2", 0);
+}
+
 // Two restart Chebyshev sweeps in one pass; *handled = false if the kernel does not apply (the caller falls back).
 int launch_heat_post2(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, double* y, double c2_0,
                       double c1_1, double c2_1, int dot_slot, bool* handled) {

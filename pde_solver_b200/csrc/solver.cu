@@ -15,6 +15,7 @@ int launch_stencil_fast(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev&
 int launch_heat_post2(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const double* b, double* y, double c2_0,
                       double c1_1, double c2_1, int dot_slot, bool* handled);
 bool elast3d_first2_ok(const Grid& g, const BcDev& bc, const OpDev& op);
+bool post2_applicable(const Grid& g, const OpDev& op);
 int launch_heat_resid_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const OpDev& op, const double* x, const double* b,
                                double* bcoarse, bool* handled);
 
@@ -456,8 +457,9 @@ static int smooth(pde_ctx* c, MGLevel& L, const double* b, double** cur, double*
     k0 = 1;
     prev_mode = 2;     // x_0 = 0
   }
-  if (!zero_guess && sweeps == 2 && L.op.dev.uniform_diag && L.op.dev.ncomp == 1 &&
-      (c->world == 1 || L.op.g.nzl >= PDE_NG)) {
+  // (the applicability test comes first: on slab levels too small for the fused kernels the two halo exchanges below
+  // would be thrown away and repeated by the sweep loop)
+  if (!zero_guess && sweeps == 2 && post2_applicable(L.op.g, L.op.dev) && (c->world == 1 || L.op.g.nzl >= PDE_NG)) {
     // both sweeps in one pass over the data (needs two halo planes of the iterate and one of the rhs)
     double c1a, c2a, c1b, c2b;
     ch.coef(0, &c1a, &c2a);
