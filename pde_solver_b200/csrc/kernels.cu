@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "device.cuh"
+#include "tma.cuh"
 
 // ----------------------------------------------------------------------------------------------
 // generic stencil kernel
@@ -452,6 +453,172 @@ k_face_rows(const __grid_constant__ Grid g, const __grid_constant__ BcDev bc, co
   }
 }
 
+// ---- k_face_tile: the 3-D three-component face rows with the neighbourhood staged by ONE TMA load per CTA ------------
+// k_face_rows keeps the 45 neighbour values of a node in registers (128 registers, 16 warps/SM) and is bound by the
+// latency of its scattered loads.  Here the CTA of a 32 x 8 face tile fetches the whole neighbourhood box - the tile grown
+// by one node in its two face directions, three layers across the face, all components - with a single
+// cp.async.bulk.tensor (out-of-domain parts arrive as zeros, ghost planes hold the halo), the class-table rows are staged
+// while it flies, and every node then works out of shared memory: a third of the registers, one bulk request instead
+// of 11 520 scattered ones per CTA.
+//   box extents (x, y, z): x faces (4, 34, 10), y faces (36, 3, 10), z faces (36, 10, 3); the x start is rounded down to an
+//   even column (TMA start coordinates must be 16-byte aligned), which the extents 4 / 36 leave room for.
+#define FT_BOX 4096   // doubles per component group: max(4*34*10, 36*3*10, 36*10*3) * 3 = 4080
+template <bool CHEBY>
+__global__ void __launch_bounds__(FACE_NT, 4)
+k_face_tile(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+            const __grid_constant__ CUtensorMap tm2, const __grid_constant__ Grid g, const __grid_constant__ BcDev bc,
+            const __grid_constant__ FaceSet fs, const double* __restrict__ coef, const double* __restrict__ dinv,
+            const double* __restrict__ load, const __grid_constant__ StencilDev a, ReduceBuf red, double* red_out) {
+  constexpr int NC = 3;
+  constexpr int ROW = PDE_NOFF * NC * NC;
+  constexpr int ROWP = (ROW + 1) / 2 * 2;
+  extern __shared__ __align__(128) double s_box[];   // FT_BOX doubles (dynamic: static shared memory ends at 48 KB)
+  constexpr int NSLOT = 8;   // class-table rows a tile can meet: face, two edges, a corner (and the interior in layer 1)
+  __shared__ __align__(16) double s_coef[NSLOT * ROWP];
+  __shared__ unsigned s_mask, s_nz[PDE_NCLASS];
+  __shared__ double s_dinv[PDE_NCLASS * NC];
+  __shared__ __align__(8) uint64_t s_bar;
+  double acc_xy = 0.0, acc_yy = 0.0;
+  const int tile = blockIdx.x;
+  int f = 0;
+#pragma unroll
+  for (int q = 1; q < 12; ++q) f += (q < fs.nface && tile >= fs.tstart[q]) ? 1 : 0;
+  const int tl = tile - fs.tstart[f];
+  const int tv = tl / fs.tiles0[f], tu = tl - tv * fs.tiles0[f];
+  const int u0 = fs.lo[f][0] + tu * FACE_TU, v0 = fs.lo[f][1] + tv * FACE_TV;   // first node of the tile
+  const int axis = fs.axis[f], fixed = fs.fixed[f];
+  // box origin (node coordinates) and extents
+  int xs, ys, zs, E0, E1, E2;
+  if (axis == 0) { xs = (fixed - 1) & ~1; ys = u0 - 1; zs = v0 - 1; E0 = 4; E1 = FACE_TU + 2; E2 = FACE_TV + 2; }
+  else if (axis == 1) { xs = (u0 - 1) & ~1; ys = fixed - 1; zs = v0 - 1; E0 = FACE_TU + 4; E1 = 3; E2 = FACE_TV + 2; }
+  else { xs = (u0 - 1) & ~1; ys = v0 - 1; zs = fixed - 1; E0 = FACE_TU + 4; E1 = FACE_TV + 2; E2 = 3; }
+  const uint32_t bar = smem_u32(&s_bar);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, (uint32_t)(E0 * E1 * E2 * NC * 8));
+    const CUtensorMap* tm = axis == 0 ? &tm0 : (axis == 1 ? &tm1 : &tm2);
+    tma_load_4d(smem_u32(s_box), tm, xs, ys, zs + PDE_NG, 0, bar);
+    s_mask = 0u;
+  }
+  const int ul = threadIdx.x & (FACE_TU - 1), vl = threadIdx.x / FACE_TU;
+  bool live = tu * FACE_TU + ul < fs.cnt[f][0] && tv * FACE_TV + vl < fs.cnt[f][1];
+  const int u = u0 + ul, v = v0 + vl;
+  int ix, iy, lz;
+  if (axis == 0) { ix = fixed; iy = u; lz = v; }
+  else if (axis == 1) { ix = u; iy = fixed; lz = v; }
+  else { ix = u; iy = v; lz = fixed; }
+  int cls = 13;
+  if (live) {
+    double bcv;
+    if (bc_node(g, bc, ix, iy, lz + g.z0, &bcv)) live = false;  // Dirichlet rows were written (masked) by the main kernel
+    cls = node_class(g, ix, iy, lz + g.z0);
+  }
+  const long long idxl = live ? (long long)g.PX * iy + g.plane * lz + ix : 0;
+  // own right-hand side / previous iterate: the only scattered loads left (issued before the staging below)
+  double bv[NC], pv[NC];
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    bv[i] = a.b ? (a.b + i * g.comp_stride)[idxl] : 0.0;
+    pv[i] = (CHEBY && a.prev_mode == 1) ? (a.xprev + i * g.comp_stride)[idxl] : 0.0;
+  }
+  if (CHEBY && a.first2)
+    for (int e = threadIdx.x; e < PDE_NCLASS * NC; e += blockDim.x) s_dinv[e] = __ldg(dinv + e);
+  if (threadIdx.x < PDE_NCLASS) s_nz[threadIdx.x] = 0u;
+  __syncthreads();
+  const unsigned mine = __reduce_or_sync(0xffffffffu, live ? (1u << cls) : 0u);
+  if ((threadIdx.x & 31) == 0 && mine) atomicOr(&s_mask, mine);
+  __syncthreads();
+  const unsigned cmask = s_mask;
+  const bool slots_ok = __popc(cmask) <= NSLOT;       // always, by the geometry of a 2-D tile; otherwise read the table
+  if (slots_ok) {
+    int slot = 0;
+    for (unsigned m = cmask; m; m &= m - 1, ++slot) {
+      const int k = __ffs(m) - 1;
+      for (int e = threadIdx.x; e < ROW; e += blockDim.x) {
+        const double cv = __ldg(coef + (size_t)k * ROW + e);
+        s_coef[slot * ROWP + e] = cv;
+        if (cv != 0.0) atomicOr(&s_nz[k], 1u << (e / (NC * NC)));
+      }
+    }
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  if (live) {
+    const int E01 = E0 * E1, EC = E01 * E2;
+    const double* const nb = s_box + (ix - xs) + E0 * (iy - ys) + E01 * (lz - zs);   // this node in the box, component 0
+    const double* cf = slots_ok ? s_coef + __popc(cmask & ((1u << cls) - 1u)) * ROWP : coef + (size_t)cls * ROW;
+    const unsigned nz = slots_ok ? s_nz[cls] : 0x7fffu;
+    const bool f2 = CHEBY && a.first2;
+    double acc[NC] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < PDE_NOFF; ++k) {
+      if (!((nz >> k) & 1u)) continue;
+      const int off = kOffDcomp(k, 0) + E0 * kOffDcomp(k, 1) + E01 * kOffDcomp(k, 2);
+      double xk[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) xk[j] = nb[off + j * EC];
+      if (f2) {   // the box holds the right-hand side: x1 = s0 D^-1 b with the class diagonal of the neighbour
+        const int jx = ix + kOffDcomp(k, 0), jy = iy + kOffDcomp(k, 1), jz = lz + g.z0 + kOffDcomp(k, 2);
+        const bool in = jx >= 0 && jx < g.nn[0] && jy >= 0 && jy < g.nn[1] && jz >= 0 && jz < g.nzg;
+        const int ck = in ? node_class(g, jx, jy, jz) : 13;
+#pragma unroll
+        for (int j = 0; j < NC; ++j) xk[j] *= a.s0 * s_dinv[ck * NC + j];
+      }
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[i] = fma(cf[k * NC * NC + i * NC + j], xk[j], acc[i]);
+    }
+    const double ld = a.b ? 0.0 : __ldg(load + cls);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const double xo = nb[i * EC];
+      const double B = a.b ? bv[i] : a.bconst[i] * ld;
+      if (f2) {
+        const double x1 = a.s0 * s_dinv[cls * NC + i] * xo;
+        (a.y + i * g.comp_stride)[idxl] = fma(1.0 + a.c1, x1, a.c2 * s_dinv[cls * NC + i] * (xo - acc[i]));
+      } else if (CHEBY) {
+        const double dprev = a.prev_mode == 1 ? xo - pv[i] : (a.prev_mode == 2 ? xo : 0.0);
+        const double dn = a.c1 * dprev + a.c2 * __ldg(dinv + cls * NC + i) * (B - acc[i]);
+        const double yv = xo + dn;
+        (a.y + i * g.comp_stride)[idxl] = yv;
+        acc_xy = fma(B, yv, acc_xy);
+      } else {
+        const double yv = a.bscale * B + a.ascale * acc[i];
+        if (a.y) (a.y + i * g.comp_stride)[idxl] = yv;
+        acc_xy = fma(xo, yv, acc_xy);
+        acc_yy = fma(yv, yv, acc_yy);
+      }
+    }
+  }
+  if (a.do_reduce && a.defer) {
+    __shared__ double sm2[2][FACE_NT / 32];
+    double vv[2] = {acc_xy, acc_yy};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) vv[i] += __shfl_down_sync(0xffffffffu, vv[i], o);
+      if ((threadIdx.x & 31) == 0) sm2[i][threadIdx.x >> 5] = vv[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < FACE_NT / 32; ++w) t += sm2[threadIdx.x][w];
+      a.defer[(size_t)blockIdx.x * RED_MAX_VALS + threadIdx.x] = t;
+    }
+  } else if (a.do_reduce) {
+    if (CHEBY) {
+      double vv[1] = {acc_xy};
+      block_reduce_finalize<1, true>(vv, red, red_out);
+    } else {
+      double vv[2] = {acc_xy, acc_yy};
+      block_reduce_finalize<2, true>(vv, red, red_out);
+    }
+  }
+}
+
 int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op, const StencilArgs& a, int* defer_blocks) {
   if (defer_blocks) *defer_blocks = 0;
   // fused first sweeps (cheby == 2): x1 = s0 D^-1 b needs the class diagonal of every neighbour, so the layer NEXT to a
@@ -511,6 +678,24 @@ int launch_face_rows(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& op
   for (int k = 0; full && k < PDE_NOFF; ++k) full = g.kidx[k] == k;
   if (layers == 2 && !full) PDE_FAIL("fused first sweeps on natural faces: grid too large for the 3-D face kernel");
   double* out = sd.do_reduce ? c->scal + a.reduce_slot_xy : nullptr;
+  static const int face_tma = getenv("PDE_B200_FACE_TMA") ? atoi(getenv("PDE_B200_FACE_TMA")) : 1;
+  if (face_tma && full && op.ncomp == 3) {
+    CUtensorMap t0, t1, t2;
+    PDE_OK(field_tensor_map(a.x, g, 3, 4, FACE_TU + 2, &t0, FACE_TV + 2));
+    PDE_OK(field_tensor_map(a.x, g, 3, FACE_TU + 4, 3, &t1, FACE_TV + 2));
+    PDE_OK(field_tensor_map(a.x, g, 3, FACE_TU + 4, FACE_TV + 2, &t2, 3));
+    static bool attr = false;
+    if (!attr) {
+      CUDA_OK(cudaFuncSetAttribute(k_face_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_BOX * 8));
+      CUDA_OK(cudaFuncSetAttribute(k_face_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_BOX * 8));
+      attr = true;
+    }
+    if (a.cheby) k_face_tile<true><<<blocks, FACE_NT, FT_BOX * 8, c->stream>>>(t0, t1, t2, g, bc, fs, op.coef, op.dinv, op.load, sd, c->red, out);
+    else k_face_tile<false><<<blocks, FACE_NT, FT_BOX * 8, c->stream>>>(t0, t1, t2, g, bc, fs, op.coef, op.dinv, op.load, sd, c->red, out);
+    c->launches++;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
 #define FACE_LAUNCH(CH, FU)                                                                                      \
   DISPATCH_NC(op.ncomp, (k_face_rows<NC, CH, FU><<<blocks, FACE_NT, 0, c->stream>>>(g, bc, fs, op.coef, op.dinv, op.load, \
                                                                                sd, c->red, out)))

@@ -652,7 +652,7 @@ static PFN_tmEncodeTiled tm_encode_fn() {
 
 struct TmKey {
   const void* base;
-  int nn0, nn1, nz, nc, bx, by;
+  int nn0, nn1, nz, nc, bx, by, bz;
   long long px, plane, cs;
   bool operator<(const TmKey& o) const {
     if (base != o.base) return base < o.base;
@@ -662,6 +662,7 @@ struct TmKey {
     if (nc != o.nc) return nc < o.nc;
     if (bx != o.bx) return bx < o.bx;
     if (by != o.by) return by < o.by;
+    if (bz != o.bz) return bz < o.bz;
     if (px != o.px) return px < o.px;
     if (plane != o.plane) return plane < o.plane;
     return cs < o.cs;
@@ -669,10 +670,10 @@ struct TmKey {
 };
 
 // Tensor map of a padded field: (x, y, z incl. the ghost planes, component); out-of-range x/y -> 0.
-int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by, CUtensorMap* out) {
+int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by, CUtensorMap* out, int bz) {
   static std::map<TmKey, CUtensorMap> cache;
   static std::mutex mu;
-  TmKey k{(const void*)field, g.nn[0], g.nn[1], g.nzl + 2 * PDE_NG, nc, bx, by, g.PX, g.plane, g.comp_stride};
+  TmKey k{(const void*)field, g.nn[0], g.nn[1], g.nzl + 2 * PDE_NG, nc, bx, by, bz, g.PX, g.plane, g.comp_stride};
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(k);
   if (it != cache.end()) { *out = it->second; return 0; }
@@ -680,7 +681,7 @@ int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by,
   if (!enc) PDE_FAIL("cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t dims[4] = {(cuuint64_t)g.nn[0], (cuuint64_t)g.nn[1], (cuuint64_t)(g.nzl + 2 * PDE_NG), (cuuint64_t)nc};
   cuuint64_t strides[3] = {(cuuint64_t)g.PX * 8, (cuuint64_t)g.plane * 8, (cuuint64_t)g.comp_stride * 8};
-  cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1u, (cuuint32_t)nc};
+  cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)nc};
   cuuint32_t es[4] = {1, 1, 1, 1};
   void* base = (void*)(field - PDE_NG * g.plane);  // first ghost plane below local plane 0
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

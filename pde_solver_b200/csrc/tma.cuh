@@ -48,7 +48,8 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // Tensor map of a padded field: (x, y, z incl. the ghost planes, component); out-of-range x/y read as 0 and are
 // clipped on stores.  Cached per (base, grid, box).
-int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by, CUtensorMap* out);
+// bz: planes per box (the sweeps load one plane at a time; the face kernel loads a whole neighbourhood).
+int field_tensor_map(const double* field, const Grid& g, int nc, int bx, int by, CUtensorMap* out, int bz = 1);
 
 static inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
