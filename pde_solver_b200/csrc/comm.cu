@@ -133,15 +133,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void wait_flag(const unsigned long long* p, unsigned long long want, int* err) {
+// returns false if the wait gave up (timeout, or another wait had already timed out)
+__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want, int* err) {
   // bounded: a lost neighbour must not hang the GPU.  After about a minute the error flag is raised (the host
-  // fails at its next poll) and every later wait returns at once.
+  // fails at its next poll) and every later wait returns at once.  `err` is mapped HOST memory: it is only looked at
+  // every 1024 polls of a wait that is not being served.
   for (long long it = 0; it < (1LL << 26); ++it) {
-    if (ld_acquire_sys(p) >= want) return;
-    if ((it & 1023) == 1023 && *(volatile int*)err) return;
+    if (ld_acquire_sys(p) >= want) return true;
+    if ((it & 1023) == 1023 && *(volatile int*)err) return false;
     __nanosleep(40);
   }
   *(volatile int*)err = 1;
+  return false;
 }
 
 // grid-stride copy of n2 double2 with four independent loads in flight per thread
@@ -160,6 +163,7 @@ __device__ __forceinline__ void copy_d2(double2* __restrict__ d, const double2* 
 
 __global__ void __launch_bounds__(256)
 k_halo_p2p(const __grid_constant__ HaloArgs a) {
+  __shared__ int s_dead;
   const bool lo = a.out_lo != nullptr, hi = a.out_hi != nullptr;
   const long long n2 = a.n >> 1;   // planes are multiples of 4 doubles
   const long long gsz = (long long)gridDim.x * blockDim.x, g0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,13 +194,15 @@ k_halo_p2p(const __grid_constant__ HaloArgs a) {
       if (lo) st_release_sys(a.lo_flags + F_ARR1, a.seq);
       if (hi) st_release_sys(a.hi_flags + F_ARR0, a.seq);
     }
-    if (lo) wait_flag(a.my_flags + F_ARR0, a.seq, a.err);
-    if (hi) wait_flag(a.my_flags + F_ARR1, a.seq, a.err);
+    bool ok = true;
+    if (lo) ok = wait_flag(a.my_flags + F_ARR0, a.seq, a.err) && ok;
+    if (hi) ok = wait_flag(a.my_flags + F_ARR1, a.seq, a.err) && ok;
+    s_dead = ok ? 0 : 1;
   }
   __syncthreads();
-  // a wait that timed out leaves stale inbox slots: do not move them into the ghost planes (the host fails at its next
+  // a wait that gave up leaves stale inbox slots: do not move them into the ghost planes (the host fails at its next
   // poll; nothing computed from them may reach an output that is fetched without one)
-  const bool dead = *(volatile int*)a.err != 0;
+  const bool dead = s_dead != 0;
   for (int c = 0; c < a.ncomp && !dead; ++c) {
     if (lo) {
       copy_d2<true>(reinterpret_cast<double2*>(a.ghost_lo + c * a.comp_stride),
