@@ -241,6 +241,7 @@ int pde_op_bench(pde_ctx* ctx, const pde_op_params* p, int reps, int warmup, dou
  * specialised sweep kernels against the generic kernel and the oracle matrix).
  *   mode 0: y = A x   1: y = b - A x   2: y = x + c2 D^-1 (b - A x)
  *   mode 3: y = x + c1 (x - xprev) + c2 D^-1 (b - A x)   4: as 3 with xprev = 0
+ *   mode 5: the fused first two sweeps from a zero guess: x1 = c2 D^-1 b, y = (1 + c1) x1 + c2 D^-1 (b - A x1)
  * Dirichlet rows: 0 in modes 0/1, x in modes 2..4.  dots (may be NULL) receives the fused reductions
  * (modes 0/1: x.y, y.y; modes 2..4: b.y over free rows, second value unspecified). */
 int pde_op_sweep(pde_ctx* ctx, const pde_op_params* p, int32_t mode, double c1, double c2, const double* x,

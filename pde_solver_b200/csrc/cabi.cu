@@ -717,8 +717,14 @@ extern "C" int pde_op_bench(pde_ctx* c, const pde_op_params* p, int reps, int wa
 //   mode 0: y = A x            1: y = b - A x          2: Chebyshev restart  y = x + c2 D^-1 (b - A x)
 //   mode 3: y = x + c1 (x - xprev) + c2 D^-1 (b - A x), output written over xprev as in the solver
 //   mode 4: as 3 with xprev = 0 (prev_mode 2)
+//   mode 5: the fused first two sweeps from a zero guess, x1 = c2 D^-1 b, y = x1 + c1 x1 + c2 D^-1 (b - A x1)
+//           (uniform-diagonal scalar operators, and the 3-D elasticity operator with its two-layer face kernel)
 static int sweep_args(int mode, double c1, double c2, const Field& x, const Field& b, Field& y, StencilArgs* a) {
-  if (mode < 0 || mode > 4) PDE_FAIL("sweep mode must be 0..4");
+  if (mode < 0 || mode > 5) PDE_FAIL("sweep mode must be 0..5");
+  if (mode == 5) {   // the first two sweeps from a zero guess in one pass: the input field is the right-hand side
+    a->x = b.p; a->y = y.p; a->cheby = 2; a->s0 = c2; a->c1 = c1; a->c2 = c2;
+    return 0;
+  }
   a->x = x.p; a->y = y.p;
   if (mode >= 1) a->b = b.p;
   if (mode == 1) { a->bscale = 1.0; a->ascale = -1.0; }
@@ -756,9 +762,9 @@ extern "C" int pde_op_sweep(pde_ctx* c, const pde_op_params* p, int mode, double
   StencilArgs a;
   PDE_OK(sweep_args(mode, c1, c2, G.x, fb, G.y, &a));
   a.variant = p->variant;
-  a.reduce_slot_xy = S_XY;
+  a.reduce_slot_xy = mode == 5 ? -1 : S_XY;
   CUDA_OK(cudaMemsetAsync(c->scal + S_XY, 0, 2 * sizeof(double), c->stream));
-  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, G.x.p));
+  if (c->world > 1) PDE_OK(comm_halo_exchange(c, g, nc, mode == 5 ? fb.p : G.x.p));
   PDE_OK(launch_stencil(c, g, G.A.bc, G.A.dev, a));
   if (dots) PDE_OK(read_scal(c, S_XY, 2, dots));
   PDE_OK(launch_pack(c, g, nc, G.y.p, (double*)dense.p, 0));

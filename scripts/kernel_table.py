@@ -19,9 +19,11 @@ BYTES = [
     (r"k_sweep3d<1, 4, 1", 24, "heat residual"),
     (r"k_sweep3d<1, 4, 2", 24, "heat Chebyshev sweep (restart form; 32 with x_prev)"),
     (r"k_sweep3d<1, 4, 3", 16, "heat first two sweeps fused (zero guess)"),
-    (r"k_heat_post2<64", 24, "heat two post-smoothing sweeps in one pass"),
+    (r"k_heat_post2<64, 4, 0", 24, "heat two post-smoothing sweeps in one pass"),
+    (r"k_heat_post2<64, 4, 1", 17, "heat residual + restriction in one pass"),
     (r"k_post2<", 24, "round-1 fused post sweeps"),
     (r"k_elast3d<0", 16, "elasticity operator apply (+ fused p.Ap)"),
+    (r"k_elast3d<3", 16, "elasticity first two sweeps fused (zero guess)"),
     (r"k_elast3d<1", 24, "elasticity residual"),
     (r"k_elast3d<2, 0", 24, "elasticity Chebyshev sweep (restart / zero x_prev)"),
     (r"k_elast3d<2, 1", 32, "elasticity Chebyshev sweep with x_prev"),
@@ -65,7 +67,8 @@ def table(path, dofs):
                 e["what"] = what
                 if b:
                     # scalar kernels of the vector solve (projection) run on dofs / 3 nodes
-                    nd = dofs / 3 if (k.endswith("<1>") and dofs % 3 == 0 and "elast" in path) else dofs
+                    scalar = k.endswith("<1>") or k.startswith("k_sweep3d<1") or k.startswith("k_face_rows<1")
+                    nd = dofs / 3 if (scalar and dofs % 3 == 0 and "elast" in path) else dofs
                     if "k_cell_rhs" in k:
                         nd = dofs / 3
                     e["bytes_per_dof"] = b
