@@ -3,7 +3,8 @@
 Times what the reference's hot loop does on every backward-Euler step through DOLFIN/PETSc
 (`solve(a == L_form, u_sol, bcs)`, fenics_mcp_server.py:709): assemble A, assemble b,
 apply the Dirichlet rows, sparse direct LU factorisation + solve — restated with SciPy/SuperLU
-because FEniCS is not installable here.  SciPy's assembly, SpMV and SuperLU are single-threaded."""
+because FEniCS is not installable here.  SciPy's assembly, SpMV and SuperLU are serial (BLAS calls inside may thread);
+bench.py reports the measured CPU time / wall time as `cores`."""
 import time
 
 import numpy as np
@@ -51,7 +52,8 @@ class HeatCsrCg3D(HeatReference3D):
     """The same time step with a Krylov solver instead of LU: A = M + dt*kappa*K assembled
     ONCE into CSR (the set-up is not timed), symmetric Dirichlet elimination, Jacobi-PCG to rtol 1e-10 from the warm
     start u_n - what `solve(..., solver_parameters={"linear_solver": "cg", "preconditioner": "jacobi"})` would do
-    per step.  SciPy's CSR SpMV is single-threaded: cores = 1."""
+    per step.  SciPy's CSR SpMV is serial, NumPy's vector operations may use several BLAS threads: bench.py reports
+    the measured CPU time / wall time as `cores`."""
 
     def __init__(self, n, rtol=1e-10, **kw):
         super().__init__(n, **kw)

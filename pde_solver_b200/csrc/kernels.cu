@@ -1019,8 +1019,9 @@ k_prolong_add(const __grid_constant__ Grid gf, const __grid_constant__ Grid gc, 
   const int nzr = gf.nzl + 2 * ghost;
   const unsigned npair = (unsigned)(gf.nn[0] + 1) / 2;
   const long long total = (long long)gf.nn[1] * nzr * npair;
+  const bool small = total < (1LL << 32);   // 32-bit index arithmetic (a 64-bit division costs ~100 instructions per pair)
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const unsigned row = (unsigned)(t / npair);
+    const unsigned row = small ? (unsigned)t / npair : (unsigned)(t / npair);
     const int k = (int)(t - (long long)row * npair);
     const int iy = (int)(row % (unsigned)gf.nn[1]);
     const int lz = (int)(row / (unsigned)gf.nn[1]) - ghost;
