@@ -113,3 +113,30 @@ def test_reference_arm_under_torchrun_prints_once():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def test_tool_pool_wire_format_and_slab_offsets():
+    """pde_solver_b200/multi.py (PDE_B200_GPUS=N): length-prefixed pickle frames over pipes; every rank's slab is a
+    contiguous range of the natural (z-slowest) vertex order and the ranges tile the global array exactly."""
+    import io
+
+    from pde_solver_b200 import _lib, multi
+    buf = io.BytesIO()
+    msgs = [{"kind": "heat", "p": b"\\x00" * 100, "nsnap": 3, "nv": 17, "shm": ["a"]}, ("ok", ({"iters_total": 5}, [0.0, 0.1]))]
+    for m in msgs:
+        multi._send(buf, m)
+    buf.seek(0)
+    assert [multi._recv(buf) for _ in msgs] == msgs
+    with pytest.raises(EOFError):
+        multi._recv(buf)
+    for n, world in (([8, 6, 16], 2), ([5, 4, 24], 4), ([3, 3, 17], 8)):
+        plane = (n[0] + 1) * (n[1] + 1)
+        nxt = 0
+        for r in range(world):
+            off, nloc, nglob = multi._slab(n, r, world)
+            assert off == nxt and nloc > 0 and nglob == plane * (n[2] + 1)
+            z0, nzl, nzg = _lib.slab_partition(3, n, r, world)
+            assert (off, nloc) == (z0 * plane, nzl * plane)
+            nxt = off + nloc
+        assert nxt == plane * (n[2] + 1)
+    assert not multi.usable(16, world=1) and multi.usable(16, world=4) and not multi.usable(15, world=4)
