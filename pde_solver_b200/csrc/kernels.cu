@@ -967,42 +967,44 @@ int launch_cheby_first(pde_ctx* c, const Grid& g, const BcDev& bc, const OpDev& 
 
 // R = P^T : coarse node C gathers r_f(2C) + 1/2 sum over the 14 (6, 2) Kuhn edge directions
 template <int NC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_restrict(const __grid_constant__ Grid gf, const __grid_constant__ Grid gc, const __grid_constant__ BcDev bcc,
            const double* __restrict__ rf, double* __restrict__ bc_out) {
-  const long long rows = (long long)gc.nn[1] * gc.nzl;
-  for (long long row = (long long)blockIdx.x * blockDim.y + threadIdx.y; row < rows;
-       row += (long long)gridDim.x * blockDim.y) {
-    const int iy = (int)(row % gc.nn[1]);
-    const int lz = (int)(row / gc.nn[1]);
+  // flat over the coarse nodes (a row-per-block mapping idles a sixth of the threads on 641-node rows), 32-bit index
+  // arithmetic while the level is small enough
+  const unsigned n0 = (unsigned)gc.nn[0], n1 = (unsigned)gc.nn[1];
+  const long long total = (long long)n0 * n1 * gc.nzl;
+  const bool small = total < (1LL << 32);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const unsigned row = small ? (unsigned)t / n0 : (unsigned)(t / n0);
+    const int ix = (int)(t - (long long)row * n0);
+    const int iy = (int)(row % n1);
+    const int lz = (int)(row / n1);
     const int gz = lz + gc.z0;
     const long long cbase = (long long)gc.PX * iy + gc.plane * lz;
     const int fy = gf.nc[1] > 0 ? 2 * iy : 0;
     const int flz = (gf.nc[2] > 0 ? 2 * gz : 0) - gf.z0;
-    const long long fbase = (long long)gf.PX * fy + gf.plane * flz;
-    for (int ix = threadIdx.x; ix < gc.nn[0]; ix += blockDim.x) {
-      double bcv;
-      const bool isdir = bc_node(gc, bcc, ix, iy, gz, &bcv);
-      const long long fi = fbase + 2 * ix;
+    const long long fi = (long long)gf.PX * fy + gf.plane * flz + 2 * ix;
+    double bcv;
+    const bool isdir = bc_node(gc, bcc, ix, iy, gz, &bcv);
 #pragma unroll
-      for (int i = 0; i < NC; ++i) {
-        double s = 0.0;
-        if (!isdir) {
-          const double* rp = rf + i * gf.comp_stride;
-          double nb = 0.0;
-          for (int k = 1; k < gf.nk; ++k) nb += rp[fi + gf.koff[k]];
-          s = rp[fi] + 0.5 * nb;
-        }
-        bc_out[cbase + ix + i * gc.comp_stride] = s;
+    for (int i = 0; i < NC; ++i) {
+      double s = 0.0;
+      if (!isdir) {
+        const double* rp = rf + i * gf.comp_stride;
+        double nb = 0.0;
+        for (int k = 1; k < gf.nk; ++k) nb += rp[fi + gf.koff[k]];
+        s = rp[fi] + 0.5 * nb;
       }
+      bc_out[cbase + ix + i * gc.comp_stride] = s;
     }
   }
 }
 
 int launch_restrict(pde_ctx* c, const Grid& gf, const Grid& gc, const BcDev& bcc, int ncomp, const double* rf,
                     double* bcoarse) {
-  RowLaunch rl = row_launch(c, gc);
-  DISPATCH_NC(ncomp, (k_restrict<NC><<<rl.grid, rl.block, 0, c->stream>>>(gf, gc, bcc, rf, bcoarse)));
+  const int blocks = flat_blocks(c, (long long)gc.nn[0] * gc.nn[1] * gc.nzl, 256);
+  DISPATCH_NC(ncomp, (k_restrict<NC><<<blocks, 256, 0, c->stream>>>(gf, gc, bcc, rf, bcoarse)));
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
