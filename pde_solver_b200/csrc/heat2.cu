@@ -26,7 +26,13 @@
 
 namespace {
 
-constexpr int H_STAGES = 4;
+// pipeline stages: the post sweeps read the two older stages in stage B (x0 own, b own) and need four; the residual /
+// restriction mode only ever reads the current one and runs with three (a fourth CTA per SM fits then)
+#ifndef H_RR_STAGES
+#define H_RR_STAGES 3
+#endif
+template <bool RR>
+struct HS { static constexpr int N = RR ? H_RR_STAGES : 4; };
 
 template <int CW, int YSB>
 struct HG {
@@ -37,7 +43,7 @@ struct HG {
   static constexpr int STAGE = XS + BS;
   static constexpr int RING = RA * CW;                                // one d0 plane of the grown tile
   static constexpr int NT = 2 * CW;
-  static constexpr size_t SMEM = ((size_t)H_STAGES * STAGE + 4 * RING) * sizeof(double) + H_STAGES * sizeof(uint64_t);   // four ring slots
+  static constexpr size_t smem(int nst) { return ((size_t)nst * STAGE + 4 * RING) * sizeof(double) + nst * sizeof(uint64_t); }   // four ring slots
 };
 
 struct H2Coef {
@@ -90,12 +96,13 @@ __device__ __forceinline__ void h2_contrib(const H2Coef& C, const double (&V)[YS
 //   tile, r(2X,2Y,2Z) + 1/2 (its 14 Kuhn neighbours), from the three ring planes around it: 17 B per fine dof (x, b in, 1/8
 //   out) instead of 24 (residual) + 9 (restriction).  Four ring slots: stage B reads the plane stage A wrote two steps ago.
 template <int CW, int YSB, bool RR>
-__global__ void __launch_bounds__(2 * CW, CW == 64 ? (YSB >= 4 ? 3 : (YSB == 3 ? 4 : 5)) : 6)
+__global__ void __launch_bounds__(2 * CW, CW == 64 ? ((RR && H_RR_STAGES == 3) ? 4 : (YSB >= 4 ? 3 : (YSB == 3 ? 4 : 5))) : 6)
 k_heat_post2(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
              const __grid_constant__ H2Coef C, const __grid_constant__ H2Args a, const __grid_constant__ H2Geom ge,
              ReduceBuf red, double* red_out) {
   using G = HG<CW, YSB>;
   constexpr int YSA = G::YSA;
+  constexpr int H_STAGES = HS<RR>::N;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* const stage0 = reinterpret_cast<double*>(smem_raw);
   double* const ring0 = stage0 + H_STAGES * G::STAGE;
@@ -280,7 +287,7 @@ int launch_t(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const
   auto kern = k_heat_post2<CW, YSB, RR>;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem(HS<RR>::N)));
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
@@ -291,7 +298,7 @@ int launch_t(pde_ctx* c, const Grid& g, const OpDev& op, const double* x0, const
   const double* h = op.h_int;
   C.c0 = h[0]; C.cxp = h[1]; C.cxm = h[2]; C.cyp = h[3]; C.cym = h[4]; C.czp = h[5]; C.czm = h[6]; C.cxyp = h[7];
   C.cxym = h[8]; C.cxzp = h[9]; C.cxzm = h[10]; C.cyzp = h[11]; C.cyzm = h[12]; C.cdp = h[13]; C.cdm = h[14];
-  kern<<<(unsigned)items, G::NT, G::SMEM, c->stream>>>(tmx, tmb, C, ha_in, ge, c->red, ha_in.do_reduce ? c->scal + ha_in.do_reduce - 1 : nullptr);
+  kern<<<(unsigned)items, G::NT, G::smem(HS<RR>::N), c->stream>>>(tmx, tmb, C, ha_in, ge, c->red, ha_in.do_reduce ? c->scal + ha_in.do_reduce - 1 : nullptr);
   c->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
