@@ -259,13 +259,37 @@ static int p2p_ensure(pde_ctx* c, size_t need) {
   h->tried = true;
   h->ok = false;
   CUDA_OK(cudaStreamSynchronize(c->stream));
+  // This function is collective.  A rank whose local set-up fails must still reach every all-reduce below, or the others
+  // block forever: local failures are only recorded and the ranks agree on the outcome through the (always present) scalar
+  // slots before the exchange buffer is used.
+  int setup_fail = 0;
   if (!h->counters) {
-    CUDA_OK(cudaMalloc(&h->counters, 2 * sizeof(unsigned)));
-    CUDA_OK(cudaMemset(h->counters, 0, 2 * sizeof(unsigned)));
-    CUDA_OK(cudaMalloc(&h->xbuf, (size_t)c->world * 8 * sizeof(unsigned long long)));
-    CUDA_OK(cudaHostAlloc(&h->err_host, sizeof(int), cudaHostAllocMapped));
-    *h->err_host = 0;
-    CUDA_OK(cudaHostGetDevicePointer((void**)&h->err_dev, h->err_host, 0));
+    if (cudaMalloc(&h->counters, 2 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(h->counters, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&h->xbuf, (size_t)c->world * 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaHostAlloc(&h->err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess) {
+      setup_fail = 1;
+      cudaGetLastError();
+    } else {
+      *h->err_host = 0;
+      if (cudaHostGetDevicePointer((void**)&h->err_dev, h->err_host, 0) != cudaSuccess) { setup_fail = 1; cudaGetLastError(); }
+    }
+  }
+  {
+    double sf = (double)setup_fail;
+    CUDA_OK(cudaMemcpyAsync(c->scal + S_TMP1, &sf, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_OK(c->nccl->AllReduce(c->scal + S_TMP1, c->scal + S_TMP1, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(&sf, c->scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    if (sf != 0.0) {   // somebody could not set up: NCCL send/recv everywhere
+      if (setup_fail) {
+        if (h->counters) cudaFree(h->counters);
+        if (h->xbuf) cudaFree(h->xbuf);
+        if (h->err_host) cudaFreeHost(h->err_host);
+        h->counters = nullptr; h->xbuf = nullptr; h->err_host = nullptr; h->err_dev = nullptr;
+      }
+      return 0;
+    }
   }
   // nobody may still be writing into a mailbox that is about to disappear: a collective acts as the barrier
   CUDA_OK(cudaMemsetAsync(h->xbuf, 0, (size_t)c->world * 8 * sizeof(unsigned long long), c->stream));

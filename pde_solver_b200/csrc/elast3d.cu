@@ -157,8 +157,11 @@ __device__ __forceinline__ void e_contrib(const ECoef& C, const double (&V)[YS +
 //                 rows on AND next to natural faces are left to k_face_rows (two layers), which knows the class diagonals
 // TOUT: the output plane is staged in shared memory and written by a TMA store (which clips at the domain boundary);
 //       otherwise every thread stores its own values (no shared-memory traffic, but address arithmetic and predicates).
+#ifndef E_THREADS_PER_SM
+#define E_THREADS_PER_SM 512
+#endif
 template <int MODE, bool PREV, int YS, bool TOUT>
-__global__ void __launch_bounds__(E_NT, (YS <= 2 ? 512 : 384) / E_NT)
+__global__ void __launch_bounds__(E_NT, (YS <= 2 ? E_THREADS_PER_SM : 384) / E_NT)
 k_elast3d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmb,
           const __grid_constant__ CUtensorMap tmp, const __grid_constant__ CUtensorMap tmy,
           const __grid_constant__ ECoef C, const __grid_constant__ EArgs a, const __grid_constant__ EGeom ge,

@@ -1,7 +1,13 @@
 mkdir -p gpurun_out
-( timeout 900 python -m pytest tests -m gpu -x -q -k "manufactured or heat_3d or smoke or superposition" 2>&1 | tail -3 ) ; 
-for rep in 1 2; do for lib in ab/libpde_base.so ab/libpde_new.so; do
-  PDE_B200_LIB=$lib timeout 600 python bench.py --steps 10 --warmup 3 --no-configs --no-cpu --no-elasticity > gpurun_out/ab.json 2>gpurun_out/ab.err
-  python -c "
-import json; d=json.loads(open('gpurun_out/ab.json').read()); print('$lib', 'heat ms/step', round(d['ms_per_step'],2))"
+for rep in 1 2; do for lib in ab/libpde_base.so ab/libpde_e640.so; do
+  echo "== $lib"; PDE_B200_LIB=$lib timeout 300 python scripts/mode_bench.py elasticity 1280 256 256 --modes 0,1,3 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l); print('  ', d['mode'], d['ms'], d['GBps'])
+    except Exception: print(l.strip()[:200])"
+  PDE_B200_LIB=$lib timeout 300 python scripts/elast_bench.py 1280 256 256 --reps 1 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l); print('   solve', d['iters'], round(d['solve_ms'],1))
+    except Exception: print(l.strip()[:200])"
 done; done
