@@ -277,9 +277,9 @@ static int p2p_ensure(pde_ctx* c, size_t need) {
   }
   {
     double sf = (double)setup_fail;
-    CUDA_OK(cudaMemcpyAsync(c->scal + S_TMP1, &sf, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    NCCL_OK(c->nccl->AllReduce(c->scal + S_TMP1, c->scal + S_TMP1, 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream));
-    CUDA_OK(cudaMemcpyAsync(&sf, c->scal + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(c->scal + (S_NSLOTS - 1), &sf, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    NCCL_OK(c->nccl->AllReduce(c->scal + (S_NSLOTS - 1), c->scal + (S_NSLOTS - 1), 1, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->nccl_comm, c->stream));
+    CUDA_OK(cudaMemcpyAsync(&sf, c->scal + (S_NSLOTS - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     if (sf != 0.0) {   // somebody could not set up: NCCL send/recv everywhere
       if (setup_fail) {
