@@ -29,6 +29,8 @@ typedef struct pde_ctx pde_ctx;
 /* ---- context / errors ------------------------------------------------------------- */
 const char* pde_last_error(void);
 int pde_version(void);
+/* CUDA devices visible to this process (0 without a GPU; never fails): the tool layer checks PDE_B200_GPUS against it */
+int pde_device_count(int32_t* count);
 /* one context per GPU (one process per GPU under torchrun; a process may hold several) */
 int pde_ctx_create(int device, pde_ctx** out);
 int pde_ctx_destroy(pde_ctx* ctx);

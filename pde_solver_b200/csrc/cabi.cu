@@ -665,6 +665,14 @@ struct OpGuard {
   ~OpGuard() { A.release(); x.release(); y.release(); r.release(); w.release(); mg.release(); }
 };
 
+// CUDA devices visible to this process; 0 (not an error) without a driver or a GPU
+extern "C" int pde_device_count(int32_t* count) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (count) *count = n;
+  return 0;
+}
+
 extern "C" int pde_op_apply(pde_ctx* c, const pde_op_params* p, const double* x, double* y) {
   if (!c || !p || !x || !y) PDE_FAIL("null argument");
   CUDA_OK(cudaSetDevice(c->device));

@@ -31,8 +31,13 @@ def requested_gpus():
 
 
 def usable(n_cells_z, world=None):
-    """Multi-GPU applies when asked for and every rank gets at least four cell layers."""
-    world = world or requested_gpus()
+    """Multi-GPU applies when asked for and every rank gets at least four cell layers.  With `world` given the answer
+    is pure arithmetic (tests); otherwise PDE_B200_GPUS must not exceed the devices this process can see - a worker that
+    cannot open its GPU would leave the others waiting in the communicator set-up."""
+    if world is None:
+        world = requested_gpus()
+        if world > 1 and world > _lib.device_count():
+            raise _lib.PdeError(f"PDE_B200_GPUS={world} but only {_lib.device_count()} CUDA device(s) are visible")
     return world > 1 and n_cells_z >= 4 * world
 
 

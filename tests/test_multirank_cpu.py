@@ -140,3 +140,18 @@ def test_tool_pool_wire_format_and_slab_offsets():
             nxt = off + nloc
         assert nxt == plane * (n[2] + 1)
     assert not multi.usable(16, world=1) and multi.usable(16, world=4) and not multi.usable(15, world=4)
+
+
+def test_requested_gpus_beyond_the_visible_devices_is_refused(monkeypatch):
+    """A worker that cannot open its GPU would leave rank 0 waiting in the communicator set-up: the tool layer refuses
+    PDE_B200_GPUS > pde_device_count() up front (and never silently falls back to fewer GPUs or to the CPU)."""
+    from pde_solver_b200 import _lib, multi
+    have = _lib.device_count()
+    assert have >= 0
+    monkeypatch.setenv("PDE_B200_GPUS", str(have + 2))
+    with pytest.raises(_lib.PdeError, match="PDE_B200_GPUS"):
+        multi.usable(64)
+    monkeypatch.setenv("PDE_B200_GPUS", "1")
+    assert not multi.usable(64)
+    monkeypatch.setenv("PDE_B200_GPUS", "not-a-number")
+    assert multi.requested_gpus() == 1
