@@ -123,7 +123,12 @@ def _worker_main(rank, world, device):
     fin, fout = sys.stdin.buffer, os.fdopen(os.dup(1), "wb")
     os.dup2(2, 1)                      # whatever a library prints goes to stderr, the pipe carries only replies
     hello = _recv(fin)
-    ctx = _lib.Context(device)
+    try:                               # say whether this rank has its GPU BEFORE anyone enters the collective set-up
+        ctx = _lib.Context(device)
+    except Exception as e:  # noqa: BLE001
+        _send(fout, ("err", f"rank {rank} (device {device}): {e}"))
+        return
+    _send(fout, ("ctx", rank))
     ctx.comm_init(rank, world, hello["uid"], hello["nccl"])
     _send(fout, ("ready", rank))
     while True:
@@ -143,6 +148,7 @@ def _worker_main(rank, world, device):
 class Pool:
     def __init__(self, world):
         self.world = world
+        self.broken = False
         path = _lib.nccl_library_path()
         uid = _lib.nccl_unique_id(path)
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -155,13 +161,26 @@ class Pool:
                                   stdin=subprocess.PIPE, stdout=subprocess.PIPE, env=env, cwd=root)
             _send(pr.stdin, {"uid": uid, "nccl": path})
             self.procs.append(pr)
-        self.ctx = _lib.Context(0)
-        self.ctx.comm_init(0, world, uid, path)          # collective with the workers' comm_init
-        for pr in self.procs:
-            tag, _ = _recv(pr.stdout)
-            if tag != "ready":
-                raise _lib.PdeError("multi-GPU worker failed to start")
+        try:
+            self.ctx = _lib.Context(0)
+            for pr in self.procs:                        # every rank holds a device context before the collective
+                self._expect(pr, "ctx")
+            self.ctx.comm_init(0, world, uid, path)      # collective with the workers' comm_init
+            for pr in self.procs:
+                self._expect(pr, "ready")
+        except Exception:
+            self.close(kill=True)
+            raise
         atexit.register(self.close)
+
+    @staticmethod
+    def _expect(pr, want):
+        try:
+            tag, payload = _recv(pr.stdout)
+        except EOFError:
+            raise _lib.PdeError(f"multi-GPU worker exited during start-up (exit code {pr.poll()})") from None
+        if tag != want:
+            raise _lib.PdeError(f"multi-GPU worker failed to start: {payload}")
 
     def run(self, msg, shapes):
         """Allocate the shared result arrays, run the command on every rank, return (rank-0 result, arrays)."""
@@ -181,7 +200,11 @@ class Pool:
             except Exception as e:  # noqa: BLE001
                 err, mine = str(e), None
             for pr in self.procs:
-                tag, payload = _recv(pr.stdout)
+                try:
+                    tag, payload = _recv(pr.stdout)
+                except EOFError:                       # the rank is gone: this pool cannot serve another call
+                    tag, payload = "err", f"worker exited (exit code {pr.poll()})"
+                    self.broken = True
                 if tag != "ok":
                     err = err or payload
             if err:
@@ -192,7 +215,7 @@ class Pool:
                 s.close()
                 s.unlink()
 
-    def close(self):
+    def close(self, kill=False):
         for pr in self.procs:
             try:
                 _send(pr.stdin, {"kind": "quit"})
@@ -201,6 +224,8 @@ class Pool:
                 pass
         for pr in self.procs:
             try:
+                if kill:                               # a rank may be stuck in the communicator set-up: do not wait
+                    pr.kill()
                 pr.wait(timeout=10)
             except Exception:
                 pr.kill()
@@ -213,9 +238,9 @@ _pool = None
 def pool():
     global _pool
     world = requested_gpus()
-    if _pool is None or _pool.world != world:
+    if _pool is None or _pool.world != world or _pool.broken:
         if _pool is not None:
-            _pool.close()
+            _pool.close(kill=_pool.broken)
         _pool = Pool(world)
     return _pool
 

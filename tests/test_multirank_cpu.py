@@ -155,3 +155,27 @@ def test_requested_gpus_beyond_the_visible_devices_is_refused(monkeypatch):
     assert not multi.usable(64)
     monkeypatch.setenv("PDE_B200_GPUS", "not-a-number")
     assert multi.requested_gpus() == 1
+
+
+def test_tool_pool_reports_a_rank_without_a_device_instead_of_hanging(monkeypatch):
+    """Pool start-up handshake: every worker says whether it holds a device context BEFORE rank 0 enters the NCCL
+    communicator set-up.  Here (no GPU) the spawned rank cannot create its context: the pool must raise with the rank's
+    own message and reap the worker - not block in the collective."""
+    import time
+
+    from pde_solver_b200 import _lib, multi
+
+    class FakeContext:                       # rank 0 'has' a device; its comm_init must never be reached
+        def __init__(self, device):
+            self.device = device
+
+        def comm_init(self, *a):
+            raise AssertionError("entered the collective although a rank reported no device")
+
+    monkeypatch.setattr(_lib, "Context", FakeContext)
+    monkeypatch.setattr(_lib, "nccl_unique_id", lambda path: b"\0" * 128)
+    monkeypatch.setattr(_lib, "nccl_library_path", lambda: "libnccl.so.2")
+    t0 = time.time()
+    with pytest.raises(_lib.PdeError, match=r"rank 1 \(device 1\).*no CUDA device"):
+        multi.Pool(2)
+    assert time.time() - t0 < 120
