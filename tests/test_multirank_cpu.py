@@ -179,3 +179,35 @@ def test_tool_pool_reports_a_rank_without_a_device_instead_of_hanging(monkeypatc
     with pytest.raises(_lib.PdeError, match=r"rank 1 \(device 1\).*no CUDA device"):
         multi.Pool(2)
     assert time.time() - t0 < 120
+
+
+def test_tool_pool_start_up_and_shutdown_handshake(monkeypatch, tmp_path):
+    """The success path of the same handshake without a GPU: the spawned rank imports a stand-in device context (a
+    sitecustomize on its PYTHONPATH patches _lib.Context before multi.py runs), so 'ctx' -> collective -> 'ready' ->
+    'quit' runs over the real pipes and the worker exits cleanly."""
+    from pde_solver_b200 import _lib, multi
+    (tmp_path / "sitecustomize.py").write_text(
+        "import pde_solver_b200._lib as L\n"
+        "class C:\n"
+        "    def __init__(self, device): self.device = device\n"
+        "    def comm_init(self, rank, world, uid, path):\n"
+        "        assert (rank, world, len(uid)) == (1, 2, 128)\n"
+        "L.Context = C\n")
+    calls = []
+
+    class FakeContext:
+        def __init__(self, device):
+            calls.append(("ctx", device))
+
+        def comm_init(self, rank, world, uid, path):
+            calls.append(("comm", rank, world))
+
+    monkeypatch.setattr(_lib, "Context", FakeContext)
+    monkeypatch.setattr(_lib, "nccl_unique_id", lambda path: b"\1" * 128)
+    monkeypatch.setattr(_lib, "nccl_library_path", lambda: "libnccl.so.2")
+    monkeypatch.setenv("PYTHONPATH", str(tmp_path))
+    p = multi.Pool(2)
+    assert calls == [("ctx", 0), ("comm", 0, 2)] and len(p.procs) == 1 and not p.broken
+    pr = p.procs[0]
+    p.close()
+    assert pr.returncode == 0 and p.procs == []
